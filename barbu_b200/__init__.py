@@ -1,0 +1,12 @@
+"""barbu_b200 — B200-native hair-strand simulation behind Barbü's `Hair` interface.
+
+The package holds only what the hot path needs: csrc/ (sm_100a kernels + the C ABI of
+include/barbu_hair.h), the build recipe, and the host-side mirror of the reference interface.
+"""
+from .hair import (BH_MATH_EXACT, BH_MATH_FAST, BarbuHairError, BhParams, Hair, HairSim, PinnedBuffer, ScalpMesh,
+                   build_patch_indices, default_params, init_tangents_host, load_library, random_values,
+                   sphere_scalp_triangles)
+
+__all__ = ["BH_MATH_EXACT", "BH_MATH_FAST", "BarbuHairError", "BhParams", "Hair", "HairSim", "PinnedBuffer",
+           "ScalpMesh", "build_patch_indices", "default_params", "init_tangents_host", "load_library",
+           "random_values", "sphere_scalp_triangles"]

@@ -1,0 +1,487 @@
+// hair_capi.cu — implementation of include/barbu_hair.h on top of the kernels.
+//
+// Host-side counterpart of Hair::{setup, update, set_bounding_sphere} (src/fx/hair.cc:42-125) and of
+// PingPongBuffer (src/memory/pingpong_buffer.cc): one device allocation holding the three SoA float4
+// planes of "buffer 0", updated in place. No CPU fallback: every path below ends in a CUDA call.
+#include "../../include/barbu_hair.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hair_gen.cuh"
+#include "hair_step.cuh"
+
+// cuda_gl_interop.h needs <GL/gl.h>, which this image does not have; the two entry points we use are
+// in libcudart and take a plain GLuint (unsigned int).
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource, unsigned int buffer,
+                                                    unsigned int flags);
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) std::snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  else std::snprintf(buf, sizeof buf, "%s", what);
+  g_last_error = buf;
+  return code;
+}
+
+#define BH_CUDA(expr)                                                       \
+  do {                                                                      \
+    cudaError_t e__ = (expr);                                               \
+    if (e__ != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, #expr, e__); } \
+  } while (0)
+
+constexpr int kHostPipeStreams = 3;
+
+}  // namespace
+
+struct bh_sim {
+  int device = 0;
+  int64_t nstrands = 0;
+  int nverts = 0;
+  int64_t nvertices = 0;                 // V = S * N
+  float4* buffer0 = nullptr;             // 3 planes, layout of PingPongBuffer buffer 0
+  float4* planes[BH_NUM_PLANES] = { nullptr, nullptr, nullptr };
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaStream_t pipe[kHostPipeStreams] = { nullptr, nullptr, nullptr };
+  bh_params params;
+  bool initialized = false;              // Hair::initialized(): state present
+  int64_t launches = 0;
+  // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)
+  float* root_pos3 = nullptr;
+  float* root_nrm3 = nullptr;
+  // skinning extension
+  float* skin_rest3 = nullptr;
+  int* skin_joints4 = nullptr;
+  float* skin_weights3 = nullptr;
+  float* skin_dq = nullptr;
+  int skin_dq_cap = 0;
+  // GL interop
+  cudaGraphicsResource* gl_resource = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    if (cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bh::StepArgs make_args(const bh_sim* s, float dt, float4* pos, float4* vel, int64_t nstrands) {
+  const bh_params& p = s->params;
+  bh::StepArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.pos = pos; a.vel = vel; a.nstrands = nstrands; a.nverts = s->nverts; a.iterations = p.iterations;
+  a.dt = dt;
+  a.dt2 = dt * dt;                                   // vec3 dt*dt, cs_simulation.glsl:182
+  // force = kForceCoeff * gravity (cs:74), one fp32 product per component; wind extension added after
+  volatile float fx = p.force_coeff * p.gravity[0], fy = p.force_coeff * p.gravity[1], fz = p.force_coeff * p.gravity[2];
+  if (p.wind[0] != 0.0f || p.wind[1] != 0.0f || p.wind[2] != 0.0f) { fx = fx + p.wind[0]; fy = fy + p.wind[1]; fz = fz + p.wind[2]; }
+  a.fx = fx; a.fy = fy; a.fz = fz;
+  a.sf = p.scale; a.damp = p.damp;
+  a.cx = p.sphere[0]; a.cy = p.sphere[1]; a.cz = p.sphere[2]; a.r = p.sphere[3];
+  a.r2 = p.sphere[3] * p.sphere[3];                  // radius * radius, cs:133
+  a.use_drag = (p.drag != 0.0f) ? 1 : 0;
+  a.keep = 1.0f - p.drag;
+  a.ncaps = p.ncapsules;
+  for (int q = 0; q < p.ncapsules && q < bh::kMaxCapsules; ++q) {
+    const bh_capsule& c = p.capsules[q];
+    a.caps[q] = bh::Capsule{ c.a[0], c.a[1], c.a[2], c.b[0], c.b[1], c.b[2], c.radius };
+  }
+  return a;
+}
+
+int ensure_roots(bh_sim* s) {
+  if (!s->root_pos3) BH_CUDA(cudaMalloc(&s->root_pos3, sizeof(float) * 3 * (size_t)s->nstrands));
+  if (!s->root_nrm3) BH_CUDA(cudaMalloc(&s->root_nrm3, sizeof(float) * 3 * (size_t)s->nstrands));
+  return BH_OK;
+}
+
+int map_gl(bh_sim* s) {
+  if (!s->gl_resource) return BH_OK;
+  BH_CUDA(cudaGraphicsMapResources(1, &s->gl_resource, s->stream));
+  void* ptr = nullptr; size_t bytes = 0;
+  BH_CUDA(cudaGraphicsResourceGetMappedPointer(&ptr, &bytes, s->gl_resource));
+  if (bytes < (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4)) return fail(BH_ERR_INVALID, "GL buffer smaller than 3 planes");
+  for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = static_cast<float4*>(ptr) + (size_t)p * s->nvertices;
+  return BH_OK;
+}
+int unmap_gl(bh_sim* s) {
+  if (!s->gl_resource) return BH_OK;
+  BH_CUDA(cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream));
+  return BH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bh_last_error(void) { return g_last_error.c_str(); }
+const char* bh_version(void) { return "barbu_hair 0.1 (sm_100a)"; }
+
+void bh_default_params(bh_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->scale = 1.45f;                                   // hair.h:41 via hair.cc:108
+  p->sphere[3] = 1.0f;                                // cs:43
+  p->iterations = 8;                                  // cs:197
+  p->gravity[1] = -9.81f;                             // cs:71
+  p->force_coeff = 20.0f;                             // cs:72
+  p->damp = 0.80f;                                    // cs:102 as lane 0 evaluates it
+  p->math = BH_MATH_EXACT;
+}
+
+int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
+  if (!out) return fail(BH_ERR_INVALID, "bh_create: out is NULL");
+  *out = nullptr;
+  if (nstrands <= 0 || nverts <= 0) return fail(BH_ERR_INVALID, "bh_create: nstrands and nverts must be positive");
+  int ndev = 0;
+  BH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BH_ERR_INVALID, "bh_create: no such CUDA device");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(BH_ERR_CUDA, "bh_create: cudaSetDevice failed");
+  bh_sim* s = new (std::nothrow) bh_sim();
+  if (!s) return fail(BH_ERR_INVALID, "bh_create: out of host memory");
+  s->device = device; s->nstrands = nstrands; s->nverts = nverts; s->nvertices = nstrands * (int64_t)nverts;
+  bh_default_params(&s->params);
+  cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kHostPipeStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); bh_destroy(s); return fail(BH_ERR_CUDA, "bh_create: allocation", e); }
+  s->stream = s->own_stream;
+  for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = s->buffer0 + (size_t)p * s->nvertices;
+  *out = s;
+  return BH_OK;
+}
+
+int bh_destroy(bh_sim* s) {
+  if (!s) return BH_OK;
+  DeviceGuard g(s->device);
+  if (s->gl_resource) cudaGraphicsUnregisterResource(s->gl_resource);
+  cudaFree(s->buffer0); cudaFree(s->root_pos3); cudaFree(s->root_nrm3);
+  cudaFree(s->skin_rest3); cudaFree(s->skin_joints4); cudaFree(s->skin_weights3); cudaFree(s->skin_dq);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
+  for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
+  delete s;
+  return BH_OK;
+}
+
+int bh_set_stream(bh_sim* s, void* cuda_stream) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_set_stream: sim is NULL");
+  s->stream = static_cast<cudaStream_t>(cuda_stream);
+  return BH_OK;
+}
+
+int bh_reset_stream(bh_sim* s) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_reset_stream: sim is NULL");
+  s->stream = s->own_stream;
+  return BH_OK;
+}
+
+int bh_synchronize(bh_sim* s) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_synchronize: sim is NULL");
+  DeviceGuard g(s->device);
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  return BH_OK;
+}
+
+int bh_set_params(bh_sim* s, const bh_params* p) {
+  if (!s || !p) return fail(BH_ERR_INVALID, "bh_set_params: NULL argument");
+  if (p->iterations < 0) return fail(BH_ERR_INVALID, "bh_set_params: iterations < 0");
+  if (p->ncapsules < 0 || p->ncapsules > BH_MAX_CAPSULES) return fail(BH_ERR_INVALID, "bh_set_params: ncapsules out of range");
+  if (p->math != BH_MATH_EXACT && p->math != BH_MATH_FAST) return fail(BH_ERR_INVALID, "bh_set_params: unknown math profile");
+  s->params = *p;
+  return BH_OK;
+}
+
+int bh_get_params(const bh_sim* s, bh_params* p) {
+  if (!s || !p) return fail(BH_ERR_INVALID, "bh_get_params: NULL argument");
+  *p = s->params;
+  return BH_OK;
+}
+
+int bh_set_bounding_sphere(bh_sim* s, const float sphere[4]) {
+  if (!s || !sphere) return fail(BH_ERR_INVALID, "bh_set_bounding_sphere: NULL argument");
+  std::memcpy(s->params.sphere, sphere, 4 * sizeof(float));
+  return BH_OK;
+}
+
+int bh_upload(bh_sim* s, const float* pos4, const float* vel4, const float* tan4) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_upload: sim is NULL");
+  DeviceGuard g(s->device);
+  const size_t bytes = (size_t)s->nvertices * sizeof(float4);
+  const float* src[BH_NUM_PLANES] = { pos4, vel4, tan4 };
+  int rc = map_gl(s); if (rc) return rc;
+  for (int p = 0; p < BH_NUM_PLANES; ++p)
+    if (src[p]) BH_CUDA(cudaMemcpyAsync(s->planes[p], src[p], bytes, cudaMemcpyHostToDevice, s->stream));
+  rc = unmap_gl(s); if (rc) return rc;
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  if (pos4) s->initialized = true;
+  return BH_OK;
+}
+
+int bh_download(bh_sim* s, float* pos4, float* vel4, float* tan4) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_download: sim is NULL");
+  DeviceGuard g(s->device);
+  const size_t bytes = (size_t)s->nvertices * sizeof(float4);
+  float* dst[BH_NUM_PLANES] = { pos4, vel4, tan4 };
+  int rc = map_gl(s); if (rc) return rc;
+  for (int p = 0; p < BH_NUM_PLANES; ++p)
+    if (dst[p]) BH_CUDA(cudaMemcpyAsync(dst[p], s->planes[p], bytes, cudaMemcpyDeviceToHost, s->stream));
+  rc = unmap_gl(s); if (rc) return rc;
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  return BH_OK;
+}
+
+int bh_device_plane(bh_sim* s, int plane, void** device_ptr, uint64_t* nbytes) {
+  if (!s || plane < 0 || plane >= BH_NUM_PLANES || !device_ptr) return fail(BH_ERR_INVALID, "bh_device_plane: bad argument");
+  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_device_plane: buffer 0 is a GL buffer (only mapped during a step)");
+  *device_ptr = s->planes[plane];
+  if (nbytes) *nbytes = (uint64_t)s->nvertices * sizeof(float4);
+  return BH_OK;
+}
+
+int bh_init_strands(bh_sim* s, const float* root_pos3, const float* root_nrm3, const float* random_value, float maxlength) {
+  if (!s || !root_pos3 || !root_nrm3 || !random_value) return fail(BH_ERR_INVALID, "bh_init_strands: NULL argument");
+  DeviceGuard g(s->device);
+  int rc = ensure_roots(s); if (rc) return rc;
+  float* d_rv = nullptr;
+  const size_t S = (size_t)s->nstrands;
+  BH_CUDA(cudaMalloc(&d_rv, sizeof(float) * S));
+  cudaError_t e = cudaMemcpyAsync(s->root_pos3, root_pos3, sizeof(float) * 3 * S, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->root_nrm3, root_nrm3, sizeof(float) * 3 * S, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rv, random_value, sizeof(float) * S, cudaMemcpyHostToDevice, s->stream);
+  rc = BH_OK;
+  if (e == cudaSuccess) rc = map_gl(s);
+  if (e == cudaSuccess && rc == BH_OK) {
+    const float scaleOffset = maxlength / static_cast<float>(s->nverts);       // hair.cc:265
+    e = bh::launch_expand_strands(s->root_pos3, s->root_nrm3, d_rv, s->nstrands, s->nverts, scaleOffset,
+                                  s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->stream);
+    s->launches += 1;
+    if (e == cudaSuccess) rc = unmap_gl(s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_rv);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_init_strands", e); }
+  if (rc) return rc;
+  s->initialized = true;
+  return BH_OK;
+}
+
+int bh_init_sphere_scalp(bh_sim* s, int rows, int cols, int64_t first, const float* random_value, float maxlength) {
+  if (!s || !random_value || rows <= 0 || cols <= 0) return fail(BH_ERR_INVALID, "bh_init_sphere_scalp: bad argument");
+  if (first < 0 || first + s->nstrands > (int64_t)rows * cols) return fail(BH_ERR_INVALID, "bh_init_sphere_scalp: strand range outside the rows*cols grid");
+  DeviceGuard g(s->device);
+  int rc = ensure_roots(s); if (rc) return rc;
+  // Row / column trigonometry in double by libm, rounded to fp32 once; the device only multiplies.
+  const double kPi = 3.14159265358979323846;
+  std::vector<float> rowtab(2 * (size_t)rows), coltab(2 * (size_t)cols);
+  for (int r = 0; r < rows; ++r) {
+    const double th = kPi * ((double)r + 0.5) / (double)rows - kPi / 2.0;
+    rowtab[2 * r] = (float)std::cos(th); rowtab[2 * r + 1] = (float)std::sin(th);
+  }
+  for (int c = 0; c < cols; ++c) {
+    const double ph = 2.0 * kPi * (double)c / (double)cols;
+    coltab[2 * c] = (float)std::cos(ph); coltab[2 * c + 1] = (float)std::sin(ph);
+  }
+  float *d_row = nullptr, *d_col = nullptr, *d_rv = nullptr;
+  const size_t S = (size_t)s->nstrands;
+  cudaError_t e = cudaMalloc(&d_row, sizeof(float) * rowtab.size());
+  if (e == cudaSuccess) e = cudaMalloc(&d_col, sizeof(float) * coltab.size());
+  if (e == cudaSuccess) e = cudaMalloc(&d_rv, sizeof(float) * S);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_row, rowtab.data(), sizeof(float) * rowtab.size(), cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_col, coltab.data(), sizeof(float) * coltab.size(), cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rv, random_value, sizeof(float) * S, cudaMemcpyHostToDevice, s->stream);
+  rc = BH_OK;
+  if (e == cudaSuccess) rc = map_gl(s);
+  if (e == cudaSuccess && rc == BH_OK) {
+    e = bh::launch_sphere_roots(d_row, d_col, cols, first, s->nstrands, s->root_pos3, s->root_nrm3, s->stream);
+    const float scaleOffset = maxlength / static_cast<float>(s->nverts);
+    if (e == cudaSuccess)
+      e = bh::launch_expand_strands(s->root_pos3, s->root_nrm3, d_rv, s->nstrands, s->nverts, scaleOffset,
+                                    s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->stream);
+    s->launches += 2;
+    if (e == cudaSuccess) rc = unmap_gl(s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_row); cudaFree(d_col); cudaFree(d_rv);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_init_sphere_scalp", e); }
+  if (rc) return rc;
+  s->initialized = true;
+  return BH_OK;
+}
+
+int bh_build_patch_indices(const int32_t* tri, int64_t nfaces, int nverts, int32_t* out, int device) {
+  if (!tri || !out || nfaces < 0 || nverts < 1) return fail(BH_ERR_INVALID, "bh_build_patch_indices: bad argument");
+  if (nfaces == 0 || nverts == 1) return BH_OK;
+  // the reference keeps element values and counts in `int` (hair.cc:398-404): refuse what would wrap
+  int32_t maxidx = 0;
+  for (int64_t q = 0; q < 3 * nfaces; ++q) { if (tri[q] < 0) return fail(BH_ERR_INVALID, "negative scalp index"); if (tri[q] > maxidx) maxidx = tri[q]; }
+  if ((int64_t)nverts * maxidx + (nverts - 1) > INT32_MAX) return fail(BH_ERR_OVERFLOW, "bh_build_patch_indices: element index exceeds int32");
+  int ndev = 0;
+  BH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BH_ERR_INVALID, "bh_build_patch_indices: no such CUDA device");
+  DeviceGuard g(device);
+  const size_t nin = 3 * (size_t)nfaces, nout = 6 * (size_t)nfaces * (size_t)(nverts - 1);
+  int *d_in = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, nin * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, nout * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, tri, nin * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = bh::launch_patch_indices(d_in, nfaces, nverts, d_out, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, nout * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_build_patch_indices", e); }
+  return BH_OK;
+}
+
+int bh_step(bh_sim* s, float dt, int substeps) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_step: sim is NULL");
+  if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_step: no strand state (call bh_upload / bh_init_* first)");
+  if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step: substeps < 1");
+  DeviceGuard g(s->device);
+  int rc = map_gl(s); if (rc) return rc;
+  const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
+  const bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
+  for (int q = 0; q < substeps; ++q) {
+    BH_CUDA(bh::launch_step(a, s->params.math, s->stream));
+    s->launches += 1;
+  }
+  return unmap_gl(s);
+}
+
+int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
+  if (!s || !pos4 || !vel4) return fail(BH_ERR_INVALID, "bh_step_host: NULL argument");
+  if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step_host: substeps < 1");
+  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_step_host: buffer 0 is a GL buffer");
+  DeviceGuard g(s->device);
+  const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
+  // Strands are independent, so a slice of strands can be uploaded, stepped `substeps` times and
+  // downloaded while its neighbours are still in flight: H2D, kernels and D2H of different slices
+  // overlap on kHostPipeStreams streams (PCIe is full duplex).
+  const int64_t S = s->nstrands;
+  int64_t slice = (S + 15) / 16;
+  const int64_t min_slice = 4096;
+  if (slice < min_slice) slice = min_slice;
+  slice = (slice + 127) / 128 * 128;
+  // order after whatever is queued on the sim's stream
+  cudaEvent_t ev;
+  BH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, s->stream);
+  for (int i = 0; i < kHostPipeStreams && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s->pipe[i], ev, 0);
+  int k = 0;
+  for (int64_t first = 0; first < S && e == cudaSuccess; first += slice, ++k) {
+    const int64_t count = (S - first < slice) ? (S - first) : slice;
+    cudaStream_t st = s->pipe[k % kHostPipeStreams];
+    const size_t off = (size_t)first * s->nverts, bytes = (size_t)count * s->nverts * sizeof(float4);
+    float4* dP = s->planes[BH_PLANE_POSITION] + off;
+    float4* dV = s->planes[BH_PLANE_VELOCITY] + off;
+    e = cudaMemcpyAsync(dP, pos4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, vel4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
+    const bh::StepArgs a = make_args(s, h, dP, dV, count);
+    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, st); s->launches += 1; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vel4 + 4 * off, dV, bytes, cudaMemcpyDeviceToHost, st);
+  }
+  for (int i = 0; i < kHostPipeStreams; ++i) { cudaError_t e2 = cudaStreamSynchronize(s->pipe[i]); if (e == cudaSuccess) e = e2; }
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_step_host", e); }
+  s->initialized = true;
+  return BH_OK;
+}
+
+int bh_host_alloc(void** ptr, uint64_t nbytes) {
+  if (!ptr) return fail(BH_ERR_INVALID, "bh_host_alloc: ptr is NULL");
+  BH_CUDA(cudaMallocHost(ptr, (size_t)nbytes));
+  return BH_OK;
+}
+int bh_host_free(void* ptr) {
+  if (ptr) BH_CUDA(cudaFreeHost(ptr));
+  return BH_OK;
+}
+
+int64_t bh_launch_count(const bh_sim* s) { return s ? s->launches : 0; }
+
+int bh_set_skin(bh_sim* s, const float* rest_root_pos3, const int32_t* joints4, const float* weights3) {
+  if (!s || !rest_root_pos3 || !joints4 || !weights3) return fail(BH_ERR_INVALID, "bh_set_skin: NULL argument");
+  DeviceGuard g(s->device);
+  const size_t S = (size_t)s->nstrands;
+  if (!s->skin_rest3) BH_CUDA(cudaMalloc(&s->skin_rest3, sizeof(float) * 3 * S));
+  if (!s->skin_joints4) BH_CUDA(cudaMalloc(&s->skin_joints4, sizeof(int) * 4 * S));
+  if (!s->skin_weights3) BH_CUDA(cudaMalloc(&s->skin_weights3, sizeof(float) * 3 * S));
+  BH_CUDA(cudaMemcpyAsync(s->skin_rest3, rest_root_pos3, sizeof(float) * 3 * S, cudaMemcpyHostToDevice, s->stream));
+  BH_CUDA(cudaMemcpyAsync(s->skin_joints4, joints4, sizeof(int) * 4 * S, cudaMemcpyHostToDevice, s->stream));
+  BH_CUDA(cudaMemcpyAsync(s->skin_weights3, weights3, sizeof(float) * 3 * S, cudaMemcpyHostToDevice, s->stream));
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  return BH_OK;
+}
+
+int bh_skin_roots(bh_sim* s, const float* dq_palette, int njoints) {
+  if (!s || !dq_palette || njoints <= 0) return fail(BH_ERR_INVALID, "bh_skin_roots: bad argument");
+  if (!s->skin_rest3) return fail(BH_ERR_NOT_INITIALIZED, "bh_skin_roots: call bh_set_skin first");
+  if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_skin_roots: no strand state");
+  DeviceGuard g(s->device);
+  if (njoints > s->skin_dq_cap) {
+    cudaFree(s->skin_dq); s->skin_dq = nullptr; s->skin_dq_cap = 0;
+    BH_CUDA(cudaMalloc(&s->skin_dq, sizeof(float) * 8 * (size_t)njoints));
+    s->skin_dq_cap = njoints;
+  }
+  BH_CUDA(cudaMemcpyAsync(s->skin_dq, dq_palette, sizeof(float) * 8 * (size_t)njoints, cudaMemcpyHostToDevice, s->stream));
+  int rc = map_gl(s); if (rc) return rc;
+  BH_CUDA(bh::launch_skin_roots_dq(s->skin_rest3, s->skin_joints4, s->skin_weights3, s->skin_dq, s->nstrands, s->nverts,
+                                   s->planes[BH_PLANE_POSITION], s->stream));
+  s->launches += 1;
+  rc = unmap_gl(s); if (rc) return rc;
+  // the palette is pageable host memory owned by the caller: do not return before it was consumed
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  return BH_OK;
+}
+
+int bh_register_gl_buffer(bh_sim* s, unsigned int gl_buffer) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_register_gl_buffer: sim is NULL");
+  if (s->gl_resource) return fail(BH_ERR_INVALID, "bh_register_gl_buffer: already registered");
+  DeviceGuard g(s->device);
+  cudaGraphicsResource* res = nullptr;
+  BH_CUDA(cudaGraphicsGLRegisterBuffer(&res, gl_buffer, 0 /* cudaGraphicsRegisterFlagsNone: read + write */));
+  s->gl_resource = res;
+  // Move the current state into the GL buffer so the VAO of hair.cc:371-389 sees it.
+  float4* own[BH_NUM_PLANES] = { s->buffer0, s->buffer0 + s->nvertices, s->buffer0 + 2 * s->nvertices };
+  int rc = map_gl(s);
+  if (rc) { cudaGraphicsUnregisterResource(res); s->gl_resource = nullptr; for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p]; return rc; }
+  cudaError_t e = cudaMemcpyAsync(s->planes[0], s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+  rc = unmap_gl(s);
+  if (e != cudaSuccess) return fail(BH_ERR_CUDA, "bh_register_gl_buffer: copy into GL buffer", e);
+  return rc;
+}
+
+int bh_unregister_gl_buffer(bh_sim* s) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_unregister_gl_buffer: sim is NULL");
+  if (!s->gl_resource) return BH_OK;
+  DeviceGuard g(s->device);
+  int rc = map_gl(s);
+  if (rc == BH_OK) {
+    cudaMemcpyAsync(s->buffer0, s->planes[0], (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+    unmap_gl(s);
+    cudaStreamSynchronize(s->stream);
+  }
+  cudaGraphicsUnregisterResource(s->gl_resource);
+  s->gl_resource = nullptr;
+  for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = s->buffer0 + (size_t)p * s->nvertices;
+  return BH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// hair_host.cc — the host-evaluated parts of Hair::init_simulation (src/fx/hair.cc:236-361).
+//
+// The reference generates strand state on the host. Positions/velocities moved to the device
+// (hair_gen.cu); what stays here is what is defined by host libraries and therefore cannot be
+// reproduced bit-for-bit by device code: the glibc rand() length jitter (hair.cc:273-275) and the
+// tangent plane (hair.cc:290-328), which goes through libm sinf/cosf and glm::simplex.
+// Build with -ffp-contract=off: one rounding per written operation, like the reference's
+// -O2 -msse4.1 build (CMakeLists.txt:263-264).
+#include "../../include/barbu_hair.h"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace {
+
+// --- 2-D simplex noise as computed by glm::simplex(vec2) (GLM 0.9.9.9, gtc/noise.inl:591-645) ----
+// Ashima/McEwan "textureless" simplex noise; operation order follows GLM's vector expressions.
+inline float mod289(float x) { return x - std::floor(x * (1.0f / 289.0f)) * 289.0f; }      // detail/_noise.hpp:9-12
+inline float permute(float x) { return mod289(((x * 34.0f) + 1.0f) * x); }                  // detail/_noise.hpp:15-18
+
+float simplex2(float vx, float vy) {
+  // GLM writes T(<double literal>): the decimal is rounded to double first, then to float
+  const float Cx = static_cast<float>(0.211324865405187), Cy = static_cast<float>(0.366025403784439);
+  const float Cz = static_cast<float>(-0.577350269189626), Cw = static_cast<float>(0.024390243902439);
+  const float skew = vx * Cy + vy * Cy;                                   // dot(v, C.yy)
+  float ix = std::floor(vx + skew), iy = std::floor(vy + skew);
+  const float unskew = ix * Cx + iy * Cx;                                 // dot(i, C.xx)
+  const float x0x = vx - ix + unskew, x0y = vy - iy + unskew;
+  const bool lower = x0x > x0y;
+  const float i1x = lower ? 1.0f : 0.0f, i1y = lower ? 0.0f : 1.0f;
+  const float x1x = (x0x + Cx) - i1x, x1y = (x0y + Cx) - i1y;             // x12.xy
+  const float x2x = x0x + Cz, x2y = x0y + Cz;                             // x12.zw
+  ix = ix - 289.0f * std::floor(ix / 289.0f);                             // mod(i, 289)
+  iy = iy - 289.0f * std::floor(iy / 289.0f);
+  const float py[3] = { iy + 0.0f, iy + i1y, iy + 1.0f };
+  const float px[3] = { 0.0f, i1x, 1.0f };
+  const float cornerx[3] = { x0x, x1x, x2x }, cornery[3] = { x0y, x1y, x2y };
+  float m[3], g[3];
+  for (int c = 0; c < 3; ++c) {
+    const float p = permute(permute(py[c]) + ix + px[c]);
+    float mc = 0.5f - (cornerx[c] * cornerx[c] + cornery[c] * cornery[c]);
+    mc = mc < 0.0f ? 0.0f : mc;
+    mc = mc * mc;
+    mc = mc * mc;
+    const float pc = p * Cw;
+    const float x = 2.0f * (pc - std::floor(pc)) - 1.0f;                  // 2 * fract(p * C.w) - 1
+    const float h = std::fabs(x) - 0.5f;
+    const float a0 = x - std::floor(x + 0.5f);
+    m[c] = mc * (static_cast<float>(1.79284291400159) - static_cast<float>(0.85373472095314) * (a0 * a0 + h * h));
+    g[c] = a0 * cornerx[c] + h * cornery[c];
+  }
+  return 130.0f * ((m[0] * g[0] + m[1] * g[1]) + m[2] * g[2]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bh_random_values(unsigned seed, int64_t first, int64_t count, float* out) {
+  if (first < 0 || count < 0 || (count > 0 && !out)) return BH_ERR_INVALID;
+  srand(seed);                                                            // stands in for app.cc:96-97
+  for (int64_t j = 0; j < first; ++j) (void)rand();
+  for (int64_t j = 0; j < count; ++j)
+    out[j] = static_cast<float>(1.0 + 0.1 * (1.0 - 2.0 * static_cast<double>(rand()) / static_cast<double>(RAND_MAX)));
+  return BH_OK;
+}
+
+int bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, int64_t count, int nverts,
+                          float maxlength, float* tan4) {
+  if (!root_nrm3 || !tan4 || total <= 0 || first < 0 || count < 0 || first + count > total || nverts < 1) return BH_ERR_INVALID;
+  const int N = nverts;
+  const float inv_nroots = 1.0f / static_cast<float>(total);              // hair.cc:292
+  const float kPi = static_cast<float>(3.14159265358979323846264338327950288);             // glm::pi<float>()
+  const float scaleMaxLength = 0.125f * sqrtf(maxlength);                 // hair.cc:294
+  for (int64_t q = 0; q < count; ++q) {
+    const int64_t j = first + q;                                          // global strand index
+    const float* nr = root_nrm3 + 3 * q;
+    float* T = tan4 + 4 * (size_t)q * N;
+    const float dj = static_cast<float>(j + 1) * inv_nroots;              // hair.cc:302
+    const float n0 = 1.25f * simplex2(sinf(3.0f * dj), cosf(5.0f));       // hair.cc:305
+    float curly[3] = { cosf(n0 * 4.0f * kPi), -0.71f * n0, sinf(n0 * 2.7f * kPi) };
+    const int B = N - 1;
+    for (int c = 0; c < 3; ++c) T[c] = .15f * nr[c];                      // outer tangents, hair.cc:310-311
+    T[3] = .15f * 0.0f;
+    for (int c = 0; c < 3; ++c) T[4 * B + c] = .2f * (-nr[c] + curly[c]);
+    T[4 * B + 3] = .2f * 0.0f;
+    const float dist_AB = static_cast<float>(B);
+    const float inv_dist = 1.0f / dist_AB;
+    for (int i = 1; i < B; ++i) {                                         // inner tangents, hair.cc:316-326
+      const float di = 10.0f * static_cast<float>(B - i) / (dist_AB - 1.0f);
+      const float n = di * simplex2(sinf(43.0f * dj), cosf(5.0f * di));
+      curly[0] = -5.8f * (10.7f * cosf(n * kPi));
+      curly[1] = -5.8f * (-2.3f * n);
+      curly[2] = -5.8f * (20.5f * sinf(n * kPi));
+      const float s = 0.1f * static_cast<float>(i) * inv_dist * scaleMaxLength;
+      for (int c = 0; c < 3; ++c) T[4 * i + c] = s * curly[c];
+      T[4 * i + 3] = s * 0.0f;
+    }
+  }
+  return BH_OK;
+}
+
+int bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri) {
+  if (rows < 1 || cols < 1 || !tri) return BH_ERR_INVALID;
+  size_t t = 0;
+  for (int r = 0; r + 1 < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const int c1 = (c + 1) % cols;
+      const int32_t v00 = r * cols + c, v10 = (r + 1) * cols + c, v01 = r * cols + c1, v11 = (r + 1) * cols + c1;
+      tri[t++] = v00; tri[t++] = v10; tri[t++] = v01;
+      tri[t++] = v01; tri[t++] = v10; tri[t++] = v11;
+    }
+  return BH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+"""Python mirror of the reference's `Hair` module interface, over the C ABI of libbarbu_hair.so.
+
+Everything here is plumbing: argument marshalling into include/barbu_hair.h entry points. The
+simulation itself only exists as CUDA kernels (barbu_b200/csrc); there is no CPU path, and loading
+fails loudly when the shared library has not been built.
+
+Reference interface mirrored (src/fx/hair.h:56-78):
+    Hair::init / deinit / setup / update / set_bounding_sphere / initialized
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _build
+
+BH_OK, BH_ERR_INVALID, BH_ERR_CUDA, BH_ERR_NOT_INITIALIZED, BH_ERR_UNSUPPORTED, BH_ERR_OVERFLOW = range(6)
+BH_MATH_EXACT, BH_MATH_FAST = 0, 1
+BH_PLANE_POSITION, BH_PLANE_VELOCITY, BH_PLANE_TANGENT = 0, 1, 2
+BH_MAX_CAPSULES = 8
+
+# Every symbol include/barbu_hair.h declares (tests check the library exports all of them).
+ABI_SYMBOLS = (
+    "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
+    "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
+    "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
+    "bh_sphere_scalp_triangles", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
+    "bh_host_free", "bh_launch_count", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
+    "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
+)
+
+
+class BhCapsule(C.Structure):
+    _fields_ = [("a", C.c_float * 3), ("b", C.c_float * 3), ("radius", C.c_float)]
+
+
+class BhParams(C.Structure):
+    """struct bh_params of include/barbu_hair.h."""
+    _fields_ = [
+        ("scale", C.c_float), ("sphere", C.c_float * 4), ("iterations", C.c_int),
+        ("gravity", C.c_float * 3), ("force_coeff", C.c_float), ("damp", C.c_float), ("math", C.c_int),
+        ("wind", C.c_float * 3), ("drag", C.c_float), ("ncapsules", C.c_int),
+        ("capsules", BhCapsule * BH_MAX_CAPSULES),
+    ]
+
+
+class BarbuHairError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"barbu_hair error {code}: {message}")
+        self.code = code
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library(build_if_missing: bool = False) -> C.CDLL:
+    """dlopen barbu_b200/lib/libbarbu_hair.so. Never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build()
+        else:
+            raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(the hair simulation has no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i64, f32 = C.c_void_p, C.c_int64, C.c_float
+    sig = {
+        "bh_create": ([C.POINTER(vp), i64, C.c_int, C.c_int], C.c_int),
+        "bh_destroy": ([vp], C.c_int),
+        "bh_set_stream": ([vp, vp], C.c_int),
+        "bh_reset_stream": ([vp], C.c_int),
+        "bh_synchronize": ([vp], C.c_int),
+        "bh_default_params": ([C.POINTER(BhParams)], None),
+        "bh_set_params": ([vp, C.POINTER(BhParams)], C.c_int),
+        "bh_get_params": ([vp, C.POINTER(BhParams)], C.c_int),
+        "bh_set_bounding_sphere": ([vp, C.POINTER(f32)], C.c_int),
+        "bh_upload": ([vp, vp, vp, vp], C.c_int),
+        "bh_download": ([vp, vp, vp, vp], C.c_int),
+        "bh_device_plane": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)], C.c_int),
+        "bh_random_values": ([C.c_uint, i64, i64, vp], C.c_int),
+        "bh_init_strands": ([vp, vp, vp, vp, f32], C.c_int),
+        "bh_init_sphere_scalp": ([vp, C.c_int, C.c_int, i64, vp, f32], C.c_int),
+        "bh_init_tangents_host": ([vp, i64, i64, i64, C.c_int, f32, vp], C.c_int),
+        "bh_sphere_scalp_triangles": ([C.c_int, C.c_int, vp], C.c_int),
+        "bh_build_patch_indices": ([vp, i64, C.c_int, vp, C.c_int], C.c_int),
+        "bh_step": ([vp, f32, C.c_int], C.c_int),
+        "bh_step_host": ([vp, f32, C.c_int, vp, vp], C.c_int),
+        "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
+        "bh_host_free": ([vp], C.c_int),
+        "bh_launch_count": ([vp], i64),
+        "bh_set_skin": ([vp, vp, vp, vp], C.c_int),
+        "bh_skin_roots": ([vp, vp, C.c_int], C.c_int),
+        "bh_register_gl_buffer": ([vp, C.c_uint], C.c_int),
+        "bh_unregister_gl_buffer": ([vp], C.c_int),
+        "bh_last_error": ([], C.c_char_p),
+        "bh_version": ([], C.c_char_p),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, restype
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != BH_OK:
+        raise BarbuHairError(rc, load_library().bh_last_error().decode(errors="replace"))
+
+
+def _f32(a, shape_last: Optional[int] = None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape_last is not None and (a.ndim == 0 or a.shape[-1] != shape_last):
+        raise ValueError(f"expected trailing dimension {shape_last}, got shape {a.shape}")
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params() -> BhParams:
+    p = BhParams()
+    load_library().bh_default_params(C.byref(p))
+    return p
+
+
+def random_values(seed: int, first: int, count: int) -> np.ndarray:
+    """hair.cc:273-275 length jitter for global strands [first, first+count)."""
+    out = np.empty(count, np.float32)
+    _check(load_library().bh_random_values(seed, first, count, _ptr(out)))
+    return out
+
+
+def sphere_scalp_triangles(rows: int, cols: int) -> np.ndarray:
+    tri = np.empty((2 * (rows - 1) * cols, 3), np.int32)
+    _check(load_library().bh_sphere_scalp_triangles(rows, cols, _ptr(tri)))
+    return tri
+
+
+def build_patch_indices(tri_indices, nverts: int, device: int = 0) -> np.ndarray:
+    """Hair::init_mesh element buffer (hair.cc:397-409), computed on the GPU."""
+    tri = np.ascontiguousarray(tri_indices, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(6 * tri.shape[0] * max(nverts - 1, 0), np.int32)
+    _check(load_library().bh_build_patch_indices(_ptr(tri), tri.shape[0], nverts, _ptr(out), device))
+    return out
+
+
+def init_tangents_host(root_nrm3, total: int, first: int, nverts: int, maxlength: float = 0.5) -> np.ndarray:
+    nrm = _f32(root_nrm3, 3)
+    out = np.empty((nrm.shape[0] * nverts, 4), np.float32)
+    _check(load_library().bh_init_tangents_host(_ptr(nrm), total, first, nrm.shape[0], nverts, maxlength, _ptr(out)))
+    return out
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaMallocHost) viewed as float32 numpy."""
+
+    def __init__(self, nfloats: int):
+        self._lib = load_library()
+        self._ptr = C.c_void_p()
+        _check(self._lib.bh_host_alloc(C.byref(self._ptr), nfloats * 4))
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_float)), shape=(nfloats,))
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            self._lib.bh_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class HairSim:
+    """Thin owner of one `bh_sim` handle (one strand shard on one GPU)."""
+
+    def __init__(self, nstrands: int, nverts: int, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.nstrands, self.nverts, self.device = int(nstrands), int(nverts), int(device)
+        _check(self._lib.bh_create(C.byref(self._h), self.nstrands, self.nverts, self.device))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self._lib.bh_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def nvertices(self) -> int:
+        return self.nstrands * self.nverts
+
+    # -- parameters --------------------------------------------------------------------------
+    def get_params(self) -> BhParams:
+        p = BhParams()
+        _check(self._lib.bh_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, p: BhParams):
+        _check(self._lib.bh_set_params(self._h, C.byref(p)))
+
+    def configure(self, **kw):
+        """Update named fields of bh_params (scale=..., math=..., sphere=(x,y,z,r), ...)."""
+        p = self.get_params()
+        for k, v in kw.items():
+            cur = getattr(p, k)
+            if isinstance(cur, C.Array) and not isinstance(v, C.Array):
+                for i, x in enumerate(v):
+                    cur[i] = x
+            else:
+                setattr(p, k, v)
+        self.set_params(p)
+
+    def set_bounding_sphere(self, sphere: Sequence[float]):
+        _check(self._lib.bh_set_bounding_sphere(self._h, (C.c_float * 4)(*sphere)))
+
+    def set_stream(self, cuda_stream: int):
+        """Launch on this cudaStream_t handle (0 = the CUDA default stream)."""
+        _check(self._lib.bh_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
+    def reset_stream(self):
+        _check(self._lib.bh_reset_stream(self._h))
+
+    def synchronize(self):
+        _check(self._lib.bh_synchronize(self._h))
+
+    # -- state -------------------------------------------------------------------------------
+    def upload(self, pos4=None, vel4=None, tan4=None):
+        arrs = [None if a is None else _f32(a).reshape(-1) for a in (pos4, vel4, tan4)]
+        for a in arrs:
+            if a is not None and a.size != 4 * self.nvertices:
+                raise ValueError(f"plane must hold {self.nvertices} float4")
+        _check(self._lib.bh_upload(self._h, *[_ptr(a) for a in arrs]))
+
+    def download(self, pos=True, vel=True, tan=False):
+        outs = [np.empty((self.nvertices, 4), np.float32) if want else None for want in (pos, vel, tan)]
+        _check(self._lib.bh_download(self._h, *[_ptr(a) for a in outs]))
+        return tuple(outs)
+
+    def device_plane(self, plane: int):
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        _check(self._lib.bh_device_plane(self._h, plane, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def init_strands(self, root_pos3, root_nrm3, random_value, maxlength: float = 0.5):
+        p, n, r = _f32(root_pos3, 3), _f32(root_nrm3, 3), _f32(random_value)
+        if p.shape[0] != self.nstrands or n.shape[0] != self.nstrands or r.size != self.nstrands:
+            raise ValueError("one root position, normal and jitter value per strand")
+        _check(self._lib.bh_init_strands(self._h, _ptr(p), _ptr(n), _ptr(r), maxlength))
+
+    def init_sphere_scalp(self, rows: int, cols: int, first: int, random_value, maxlength: float = 0.5):
+        r = _f32(random_value)
+        if r.size != self.nstrands:
+            raise ValueError("one jitter value per strand of this shard")
+        _check(self._lib.bh_init_sphere_scalp(self._h, rows, cols, first, _ptr(r), maxlength))
+
+    # -- stepping ----------------------------------------------------------------------------
+    def step(self, dt: float, substeps: int = 1):
+        _check(self._lib.bh_step(self._h, dt, substeps))
+
+    def step_host(self, dt: float, substeps: int, pos4: np.ndarray, vel4: np.ndarray):
+        for a in (pos4, vel4):
+            if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != 4 * self.nvertices:
+                raise ValueError("host planes must be C-contiguous float32 with 4*V elements")
+        _check(self._lib.bh_step_host(self._h, dt, substeps, _ptr(pos4), _ptr(vel4)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bh_launch_count(self._h))
+
+    # -- extensions --------------------------------------------------------------------------
+    def set_skin(self, rest_root_pos3, joints4, weights3):
+        p, w = _f32(rest_root_pos3, 3), _f32(weights3, 3)
+        j = np.ascontiguousarray(joints4, dtype=np.int32)
+        _check(self._lib.bh_set_skin(self._h, _ptr(p), _ptr(j), _ptr(w)))
+
+    def skin_roots(self, dq_palette):
+        dq = _f32(dq_palette, 8)
+        _check(self._lib.bh_skin_roots(self._h, _ptr(dq), dq.shape[0]))
+
+    def register_gl_buffer(self, gl_buffer: int):
+        _check(self._lib.bh_register_gl_buffer(self._h, gl_buffer))
+
+    def unregister_gl_buffer(self):
+        _check(self._lib.bh_unregister_gl_buffer(self._h))
+
+
+@dataclass
+class ScalpMesh:
+    """The members of MeshData (src/memory/resources/mesh_data.h:62-92) the hair path reads."""
+    positions: np.ndarray                      # (S, 3) vertices[j].position
+    normals: np.ndarray                        # (S, 3) vertices[j].normal
+    indices: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))  # triangle list
+
+    @property
+    def nvertices(self) -> int:
+        return int(self.positions.shape[0])
+
+    @property
+    def nfaces(self) -> int:
+        return int(np.asarray(self.indices).reshape(-1, 3).shape[0])
+
+
+class Hair:
+    """Same call surface as the reference's `class Hair` for the simulation path.
+
+    init()/deinit(), setup(scalp), update(dt), set_bounding_sphere(vec4), initialized() behave as in
+    src/fx/hair.cc:26-125: `setup` with an unusable scalp logs and leaves the module uninitialised,
+    `update` before `setup` is a silent no-op. `render` stays with the reference's GL path, which
+    reads plane 0 / plane 2 of buffer 0 (hair.cc:371-389).
+    """
+
+    @dataclass
+    class Parameters:
+        maxlength: float = 0.50          # sim.maxlength, hair.h:29
+        length_scale: float = 1.450      # render.lengthScale -> uScaleFactor, hair.h:41, hair.cc:108
+        ncontrol_points: int = 4         # HAIR_MAX_PARTICLE_PER_STRAND, interop.h:8 (runtime here)
+        seed: int = 1234                 # stands in for srand(time(NULL)), app.cc:96-97
+        substeps: int = 1                # extension: 1 == reference
+        math: int = BH_MATH_EXACT
+
+    def __init__(self, device: int = 0, params: Optional["Hair.Parameters"] = None):
+        self.params = params or Hair.Parameters()
+        self.device = device
+        self.nroots = 0
+        self.sim: Optional[HairSim] = None
+        self.patch_indices: Optional[np.ndarray] = None
+        self._sphere = None
+        self.log = []
+
+    def init(self):
+        load_library()
+
+    def deinit(self):
+        if self.sim is not None:
+            self.sim.close()
+        self.sim, self.nroots, self.patch_indices = None, 0, None
+
+    def initialized(self) -> bool:
+        return self.nroots != 0
+
+    def setup(self, scalp: Optional[ScalpMesh]):
+        if scalp is None or scalp.nvertices == 0:
+            self.log.append("The scalp mesh resource was not found.")       # hair.cc:45-48
+            return
+        N = self.params.ncontrol_points
+        S = scalp.nvertices                                                 # hair.cc:58
+        self.sim = HairSim(S, N, self.device)
+        # init_simulation (hair.cc:236-361): device expansion + host tangents
+        rv = random_values(self.params.seed, 0, S)
+        self.sim.init_strands(scalp.positions, scalp.normals, rv, self.params.maxlength)
+        tan = init_tangents_host(scalp.normals, S, 0, N, self.params.maxlength)
+        self.sim.upload(tan4=tan)
+        # init_mesh (hair.cc:363-417): element buffer for the tess patches
+        if scalp.nfaces:
+            self.patch_indices = build_patch_indices(scalp.indices, N, self.device)
+        self.sim.configure(scale=self.params.length_scale, math=self.params.math)
+        if self._sphere is not None:
+            self.sim.set_bounding_sphere(self._sphere)
+        self.nroots = S
+
+    def set_bounding_sphere(self, sphere: Sequence[float]):
+        self._sphere = tuple(float(x) for x in sphere)
+        if self.sim is not None:
+            self.sim.set_bounding_sphere(self._sphere)
+
+    def update(self, dt: float):
+        if not self.initialized():
+            self.log.append("Calling Hair::update without initialization.")  # hair.cc:90-93
+            return
+        self.sim.configure(scale=self.params.length_scale)                   # uniform re-sent every frame, hair.cc:108
+        self.sim.step(dt, self.params.substeps)

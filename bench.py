@@ -1,0 +1,298 @@
+#!/usr/bin/env python3
+"""bench.py — strand-vertex updates/s of the fused hair step on B200, with roofline and CPU baseline.
+
+Contract:
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                    (the reference path on the host CPU cores)
+
+A "step" is one frame of BASELINE.json configs[1]: 2^20 strands x 32 vertices per GPU, 4 substeps
+(4 launches of the fused kernel with dt/4), sphere collider. Strands are independent, so ranks hold
+disjoint strand ranges of one (1024 x 1024*N) scalp and never communicate (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "strand_vertex_updates_per_sec"
+UNIT = "updates/s"
+ROWS, COLS_PER_GPU, NVERTS, SUBSTEPS = 1024, 1024, 32, 4       # configs[1]: 1M strands x 32, 4 substeps/frame
+DT = float(np.float32(1.0) / np.float32(90.0))                  # core/global_clock.cc:160-162
+SPHERE = (0.0, 0.0, 0.0, 0.98)
+SCALE = 1.45                                                    # reference default uScaleFactor
+BYTES_PER_VERTEX_PER_LAUNCH = 64                                # float4 pos+vel read, float4 pos+vel written
+SEED = 1234
+
+
+def workload_name(n_gpus):
+    return (f"configs[1]: synthetic sphere scalp, {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices per GPU, "
+            f"{SUBSTEPS} substeps/frame, sphere collider r=0.98, scale {SCALE}, dt 1/90")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True,
+                                         bufsize=1)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        good = [(t, r) for t, r in self.rows if len(r) >= 7 and num(r[0]) is not None]
+        # samples whose arrival time falls inside the timed region (nvidia-smi prints one line per period)
+        inside = [r for t, r in good if self.t_begin is not None and self.t_begin <= t <= self.t_end + 0.03]
+        window = "timed region"
+        if len(inside) < 2:            # region shorter than a few sampling periods: fall back to pre-roll + timed region
+            inside, window = [r for _, r in good], "pre-roll + timed region"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower() == "active" for r in inside)]
+        sm = [num(r[0]) for r in inside]
+        pw = [num(r[6]) for r in inside if num(r[6]) is not None]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(num(r[1]) for r in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "window": window, "power_w_max": max(pw) if pw else None}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_time(nstrands_sample, steps, warmup, threads):
+    """Time the reference path on the host cores: the CPU oracle (a C restatement of cs_simulation.glsl pinned
+    bit-exact to the reference shader source, oracle/_ref) on the first `nstrands_sample` strands of the workload."""
+    from oracle import pyoracle as po
+    rows = nstrands_sample // COLS_PER_GPU
+    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU)          # same scalp, first `rows` latitude rows
+    root_pos, root_nrm = root_pos[:nstrands_sample], root_nrm[:nstrands_sample]
+    rv = po.random_values(SEED, nstrands_sample)
+    pos, vel = po.init_strands(root_pos, root_nrm, rv, NVERTS)
+    h = float(np.float32(DT) / np.float32(SUBSTEPS))
+    par = po.default_params(dt=h, scale=SCALE, sphere=SPHERE)
+    for _ in range(warmup):
+        for _ in range(SUBSTEPS):
+            po.step(pos, vel, nstrands_sample, NVERTS, par, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for _ in range(SUBSTEPS):
+            po.step(pos, vel, nstrands_sample, NVERTS, par, nthreads=threads)
+    dt = time.perf_counter() - t0
+    del rows
+    return nstrands_sample * NVERTS * SUBSTEPS * steps / dt, dt / steps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    sample = 1 << 17                                                     # 1/8 of the per-GPU workload per step
+    value, s_per_step = cpu_reference_time(sample, args.steps, args.warmup, threads)
+    sample_txt = (f"first {sample} of {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices x {SUBSTEPS} substeps per step, "
+                  f"{threads} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": sample_txt,
+                   "note": "reference GLSL cannot run (no GL/EGL/OSMesa/llvmpipe in the image): CPU restatement of "
+                           "cs_simulation.glsl, bit-exact to the shader source compiled against the reference GLM"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import barbu_b200 as bb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hair simulation has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    S = ROWS * COLS_PER_GPU                       # strands of this rank
+    cols_total = COLS_PER_GPU * world             # one scalp grid ROWS x cols_total shared by all ranks
+    first = rank * S
+    V = S * NVERTS
+    math = bb.BH_MATH_FAST if args.math == "fast" else bb.BH_MATH_EXACT
+
+    sim = bb.HairSim(S, NVERTS, device=local_rank)
+    sim.configure(scale=SCALE, sphere=SPHERE, math=math)
+    sim.init_sphere_scalp(ROWS, cols_total, first, bb.random_values(SEED, first, S))
+    stream = torch.cuda.Stream()                  # a real (non-default) stream owned by torch ...
+    torch.cuda.set_stream(stream)
+    sim.set_stream(stream.cuda_stream)            # ... that our kernels are launched on, so torch events bracket them
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: value + roofline ---------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # warm-up: W untimed steps, continued for >= 0.4 s so clocks settle and the sampler has data before the timed region
+    t_w = time.perf_counter()
+    done = 0
+    while done < args.warmup or time.perf_counter() - t_w < args.preroll:
+        sim.step(DT, SUBSTEPS)
+        done += 1
+        if done % 16 == 0:
+            torch.cuda.synchronize()
+    barrier()
+    sampler.mark_begin()
+    l0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.step(DT, SUBSTEPS)
+    ev1.record(stream)
+    barrier()
+    sampler.mark_end()
+    launches = sim.launch_count - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the C ABI with HOST buffers (bh_step_host): H2D + 4 substeps + D2H per step ---
+    e2e_value, e2e_steps = None, 0
+    if not args.no_e2e:
+        hp, hv = bb.PinnedBuffer(4 * V), bb.PinnedBuffer(4 * V)
+        p0, v0, _ = sim.download()
+        hp.array[:] = p0.reshape(-1)
+        hv.array[:] = v0.reshape(-1)
+        del p0, v0
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            sim.step_host(DT, SUBSTEPS, hp.array, hv.array)      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sim.step_host(DT, SUBSTEPS, hp.array, hv.array)      # returns after the D2H copies completed
+        torch.cuda.synchronize()
+        t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_value = world * V * SUBSTEPS * e2e_steps / float(t_e2e.item())
+        hp.free(); hv.free()
+    sim.close()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch_s = ms_total * 1e-3 / launches
+        achieved = BYTES_PER_VERTEX_PER_LAUNCH * V / per_launch_s / 1e9
+        value = world * V * SUBSTEPS * args.steps / (ms_total * 1e-3)
+        threads = host_threads()
+        sample = 1 << 19
+        cpu_value, _ = cpu_reference_time(sample, 1, 0, threads) if world == 1 and not args.no_cpu_baseline else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(world), "math": args.math, "iterations": 8,
+                       "l2": "state 1 GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "hair_step_pipelined_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V, "ms_per_launch": per_launch_s * 1e3},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * V, "d2h_bytes_per_step": 32 * V,
+                    "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if cpu_value is not None:
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {sample} of {S} strands x {NVERTS} vertices x {SUBSTEPS} substeps, 1 step, "
+                                              f"{threads} OpenMP threads; CPU restatement of the reference GLSL, not llvmpipe"}
+        traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                line["roofline"]["traffic"] = json.load(f).get(args.math)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--math", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--preroll", type=float, default=0.4, help="minimum seconds of untimed warm-up (0 for profiler runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

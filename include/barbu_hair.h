@@ -1,0 +1,139 @@
+/*
+ * barbu_hair.h — C ABI of the B200-native hair-strand simulation (libbarbu_hair.so).
+ *
+ * Drop-in boundary for ONE path of tcoppex/barbu: what `class Hair` (src/fx/hair.h:24-121) does
+ * between `setup()` and the position buffer the tessellation/Marschner render path reads.
+ * Plain pointers and sizes only; no C++/torch types. Every entry point returns 0 (BH_OK) or an
+ * error code, never throws or aborts (the reference logs and returns, hair.cc:45-48,90-93).
+ * The implementation is CUDA for sm_100a only: there is no CPU fallback, and every call fails with
+ * BH_ERR_CUDA when no device is usable.
+ *
+ * Buffer contract (src/memory/pingpong_buffer.cc:16-17,44-48; src/fx/hair.cc:371-389):
+ *   one device buffer ("buffer 0" == PingPongBuffer::read_ssbo_id()) of 3 SoA planes of float4,
+ *   plane p at byte offset p * V * 16, V = nstrands * nverts, vertex index = strand * nverts + i:
+ *     plane 0  position.xyz + rest length      (SSBO_HAIR_SIM_POSITION_READ, interop.h:19)
+ *     plane 1  velocity.xyz + 0                (SSBO_HAIR_SIM_VELOCITY_READ, interop.h:20)
+ *     plane 2  tangent.xyz  + 0                (SSBO_HAIR_SIM_TANGENT_READ,  interop.h:21)
+ *   bh_step updates planes 0 and 1 IN PLACE (each strand is owned by one thread), so the
+ *   reference's WRITE buffer and its per-frame swap() copy (pingpong_buffer.cc:73-84) do not exist.
+ */
+#ifndef BARBU_HAIR_H_
+#define BARBU_HAIR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bh_sim bh_sim;   /* opaque; owns device memory, a stream and (optionally) a GL mapping */
+
+enum {
+  BH_OK = 0,
+  BH_ERR_INVALID = 1,        /* bad argument */
+  BH_ERR_CUDA = 2,           /* CUDA runtime error / no device; see bh_last_error() */
+  BH_ERR_NOT_INITIALIZED = 3,/* step before any state was uploaded/generated (Hair::initialized(), hair.h:76-78) */
+  BH_ERR_UNSUPPORTED = 4,
+  BH_ERR_OVERFLOW = 5        /* an int32 output would overflow (hair.cc:398 `int nelems`) */
+};
+
+enum { BH_PLANE_POSITION = 0, BH_PLANE_VELOCITY = 1, BH_PLANE_TANGENT = 2, BH_NUM_PLANES = 3 };
+
+/* Arithmetic profile of the step kernel.
+ * BH_MATH_EXACT: IEEE-754 binary32 operation sequence of oracle/barbu_hair_oracle.c (bit-exact).
+ * BH_MATH_FAST : FMA-contracted, MUFU.RSQ-based normalisation — the arithmetic a GPU GLSL compiler
+ *                emits for the reference shader; <= 1e-5 relative per vertex after one step. */
+enum { BH_MATH_EXACT = 0, BH_MATH_FAST = 1 };
+
+#define BH_MAX_CAPSULES 8
+typedef struct bh_capsule { float a[3]; float b[3]; float radius; } bh_capsule;
+
+typedef struct bh_params {
+  /* reference uniforms and shader constants (cs_simulation.glsl:37-43,71-74,102,197) */
+  float scale;          /* uScaleFactor  <- Hair::Parameters_t::render.lengthScale = 1.45 (hair.cc:108) */
+  float sphere[4];      /* uBoundingSphere (xyz centre, w radius), default (0,0,0,1) (cs:43) */
+  int   iterations;     /* kNumContraintsIteration = 8 */
+  float gravity[3];     /* (0, -9.81, 0) */
+  float force_coeff;    /* kForceCoeff = 20 */
+  float damp;           /* dftl_damp_scale as lane 0 evaluates it = 0.80 */
+  int   math;           /* BH_MATH_EXACT (default) or BH_MATH_FAST */
+  /* extensions with NO reference implementation; zero = off = reference behaviour */
+  float wind[3];        /* constant force added to force_coeff * gravity */
+  float drag;           /* integration uses velocity * (1 - drag) */
+  int   ncapsules;      /* capsule colliders applied after the sphere, in order */
+  bh_capsule capsules[BH_MAX_CAPSULES];
+} bh_params;
+
+/* ---- lifetime: PingPongBuffer::setup / destroy (pingpong_buffer.cc:6-33) -------------------- */
+int  bh_create(bh_sim** out, int64_t nstrands, int nverts, int device);
+int  bh_destroy(bh_sim* sim);
+/* Launch on a caller-owned cudaStream_t (e.g. the host framework's current stream) instead of the
+ * sim's own non-blocking stream. NULL is the CUDA legacy default stream, as everywhere in CUDA. */
+int  bh_set_stream(bh_sim* sim, void* cuda_stream);
+int  bh_reset_stream(bh_sim* sim);                    /* back to the sim's own stream */
+int  bh_synchronize(bh_sim* sim);
+
+/* ---- parameters: uniforms of Hair::update (hair.cc:107-110), Hair::set_bounding_sphere -------- */
+void bh_default_params(bh_params* p);
+int  bh_set_params(bh_sim* sim, const bh_params* p);
+int  bh_get_params(const bh_sim* sim, bh_params* p);
+int  bh_set_bounding_sphere(bh_sim* sim, const float sphere[4]);          /* hair.h:72-74 */
+
+/* ---- state transfer: glNamedBufferSubData per plane (hair.cc:336-340); NULL planes are skipped -- */
+int  bh_upload(bh_sim* sim, const float* pos4, const float* vel4, const float* tan4);
+int  bh_download(bh_sim* sim, float* pos4, float* vel4, float* tan4);
+/* Device address of plane p of buffer 0 (for zero-copy consumers: NCCL all-gather, CUDA renderers). */
+int  bh_device_plane(bh_sim* sim, int plane, void** device_ptr, uint64_t* nbytes);
+
+/* ---- strand generation: Hair::init_simulation (hair.cc:236-361) on the device --------------- */
+/* hair.cc:273-275: srand(seed); value j = float(1.0 + 0.1*(1.0 - 2.0*rand()/RAND_MAX)) for global
+ * strand j. Writes values [first, first+count). Host glibc rand(), exactly as the reference. */
+int  bh_random_values(unsigned seed, int64_t first, int64_t count, float* out);
+/* hair.cc:255-287 from caller-provided roots (scalp vertex position + normal, one per strand). */
+int  bh_init_strands(bh_sim* sim, const float* root_pos3, const float* root_nrm3,
+                     const float* random_value, float maxlength);
+/* Synthetic unit-sphere scalp of rows*cols strands; this sim holds global strands
+ * [first, first+nstrands). Roots are generated on the device, then expanded as bh_init_strands. */
+int  bh_init_sphere_scalp(bh_sim* sim, int rows, int cols, int64_t first,
+                          const float* random_value, float maxlength);
+/* hair.cc:290-328: tangent plane, host-evaluated (libm sinf/cosf + glm::simplex restated), for
+ * global strands [first, first+count) out of `total`. Output: count*nverts float4. */
+int  bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, int64_t count,
+                           int nverts, float maxlength, float* tan4);
+/* Triangle list of the synthetic sphere scalp: 2*(rows-1)*cols triangles, int32 x 3. */
+int  bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri_indices);
+
+/* ---- Hair::init_mesh element buffer (hair.cc:397-409), computed on the device --------------- */
+/* out: 6 * nfaces * (nverts-1) int32, host memory. */
+int  bh_build_patch_indices(const int32_t* tri_indices, int64_t nfaces, int nverts, int32_t* out, int device);
+
+/* ---- Hair::update(dt) (hair.cc:89-125) ------------------------------------------------------- */
+/* `substeps` launches of the fused step kernel, each with dt/substeps (substeps = 1: reference). */
+int  bh_step(bh_sim* sim, float dt, int substeps);
+/* Same through HOST buffers: upload pos/vel, step, download pos/vel; copies are chunked and
+ * overlapped with the kernels on internal streams. Buffers should be page-locked (bh_host_alloc). */
+int  bh_step_host(bh_sim* sim, float dt, int substeps, float* pos4, float* vel4);
+int  bh_host_alloc(void** ptr, uint64_t nbytes);     /* cudaMallocHost */
+int  bh_host_free(void* ptr);
+/* Kernel launches issued by this sim so far (bench.py's gpu_launches claim). */
+int64_t bh_launch_count(const bh_sim* sim);
+
+/* ---- extension: dual-quaternion skinned roots (formula of shared/inc_skinning.glsl:22-31,54-82) */
+/* Stores rest roots + skin data once; bh_skin_roots rewrites vertex 0 of every strand in plane 0. */
+int  bh_set_skin(bh_sim* sim, const float* rest_root_pos3, const int32_t* joints4, const float* weights3);
+int  bh_skin_roots(bh_sim* sim, const float* dq_palette, int njoints);
+
+/* ---- CUDA-GL interop on buffer 0 (pbuffer_.read_ssbo_id(), hair.cc:371) --------------------- */
+/* cudaGraphicsGLRegisterBuffer; while registered, bh_step maps the GL buffer, steps in place and
+ * unmaps, so the render VAO (hair.cc:371-389) sees the new positions without a copy. Needs a
+ * current GL context on the calling thread; returns BH_ERR_CUDA otherwise. */
+int  bh_register_gl_buffer(bh_sim* sim, unsigned int gl_buffer);
+int  bh_unregister_gl_buffer(bh_sim* sim);
+
+const char* bh_last_error(void);     /* thread-local message of the last failing call */
+const char* bh_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BARBU_HAIR_H_ */

@@ -1,0 +1,182 @@
+"""ctypes access to the CPU oracle (oracle/libbarbu_hair_oracle.so) and, when built, oracle/_ref.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. Nothing under barbu_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libbarbu_hair_oracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+BHO_MAX_COLLIDERS = 8
+
+
+class BhoCapsule(C.Structure):
+    _fields_ = [("a", C.c_float * 3), ("b", C.c_float * 3), ("radius", C.c_float)]
+
+
+class BhoParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("scale", C.c_float), ("sphere", C.c_float * 4), ("iterations", C.c_int),
+                ("gravity", C.c_float * 3), ("force_coeff", C.c_float), ("damp", C.c_float),
+                ("wind", C.c_float * 3), ("drag", C.c_float), ("ncapsules", C.c_int),
+                ("capsules", BhoCapsule * BHO_MAX_COLLIDERS)]
+
+
+def build_oracle(force: bool = False) -> str:
+    src = os.path.join(HERE, "barbu_hair_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
+    return ORACLE_SO
+
+
+def build_ref() -> bool:
+    """Build oracle/_ref from /root/reference when that tree exists (this container only)."""
+    if not os.path.isdir(os.environ.get("BARBU_REFERENCE", "/root/reference")):
+        return False
+    subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+    return True
+
+
+_oracle = None
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        _oracle = C.CDLL(build_oracle())
+        _oracle.bho_simplex2.restype = C.c_float
+        _oracle.bho_simplex2.argtypes = [C.c_float, C.c_float]
+        _oracle.bho_fnv1a64.restype = C.c_uint64
+        _oracle.bho_patch_indices.restype = C.c_int
+    return _oracle
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw) -> BhoParams:
+    p = BhoParams()
+    oracle().bho_default_params(C.byref(p))
+    for k, v in kw.items():
+        cur = getattr(p, k)
+        if isinstance(cur, C.Array):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def step(pos4: np.ndarray, vel4: np.ndarray, nstrands: int, nverts: int, params: BhoParams, nthreads: int = 1):
+    """In-place reference step on (V,4) float32 arrays."""
+    assert pos4.dtype == np.float32 and vel4.dtype == np.float32 and pos4.flags.c_contiguous and vel4.flags.c_contiguous
+    oracle().bho_step_mt(_p(pos4), _p(vel4), C.c_int64(nstrands), C.c_int(nverts), C.byref(params), C.c_int(nthreads))
+
+
+def random_values(seed: int, nstrands: int) -> np.ndarray:
+    out = np.empty(nstrands, np.float32)
+    oracle().bho_random_values(C.c_uint(seed), C.c_int64(nstrands), _p(out))
+    return out
+
+
+def sphere_scalp(rows: int, cols: int):
+    S = rows * cols
+    pos, nrm = np.empty((S, 3), np.float32), np.empty((S, 3), np.float32)
+    tri = np.empty((2 * (rows - 1) * cols, 3), np.int32)
+    oracle().bho_sphere_scalp(C.c_int(rows), C.c_int(cols), _p(pos), _p(nrm), _p(tri))
+    return pos, nrm, tri
+
+
+def init_strands(root_pos3, root_nrm3, random_value, nverts: int, maxlength: float = 0.5):
+    S = root_pos3.shape[0]
+    pos, vel = np.empty((S * nverts, 4), np.float32), np.empty((S * nverts, 4), np.float32)
+    oracle().bho_init_strands(_p(np.ascontiguousarray(root_pos3, np.float32)), _p(np.ascontiguousarray(root_nrm3, np.float32)),
+                              _p(np.ascontiguousarray(random_value, np.float32)), C.c_int64(S), C.c_int(nverts),
+                              C.c_float(maxlength), _p(pos), _p(vel))
+    return pos, vel
+
+
+def init_tangents(root_nrm3, nverts: int, maxlength: float = 0.5) -> np.ndarray:
+    S = root_nrm3.shape[0]
+    tan = np.empty((S * nverts, 4), np.float32)
+    oracle().bho_init_tangents(_p(np.ascontiguousarray(root_nrm3, np.float32)), C.c_int64(S), C.c_int(nverts),
+                               C.c_float(maxlength), _p(tan))
+    return tan
+
+
+def patch_indices(tri: np.ndarray, nverts: int) -> np.ndarray:
+    tri = np.ascontiguousarray(tri, np.int32).reshape(-1, 3)
+    out = np.empty(6 * tri.shape[0] * max(nverts - 1, 0), np.int32)
+    rc = oracle().bho_patch_indices(_p(tri), C.c_int64(tri.shape[0]), C.c_int(nverts), _p(out))
+    if rc != 0:
+        raise OverflowError("patch indices exceed int32")
+    return out
+
+
+def skin_roots_dq(rest_pos3, rest_nrm3, joints4, weights3, dq):
+    S = rest_pos3.shape[0]
+    op, on = np.empty((S, 3), np.float32), np.empty((S, 3), np.float32)
+    oracle().bho_skin_roots_dq(_p(np.ascontiguousarray(rest_pos3, np.float32)), _p(np.ascontiguousarray(rest_nrm3, np.float32)),
+                               _p(np.ascontiguousarray(joints4, np.int32)), _p(np.ascontiguousarray(weights3, np.float32)),
+                               _p(np.ascontiguousarray(dq, np.float32)), C.c_int64(S), _p(op), _p(on))
+    return op, on
+
+
+def fnv1a64(a: np.ndarray) -> int:
+    a = np.ascontiguousarray(a)
+    return int(oracle().bho_fnv1a64(_p(a), C.c_uint64(a.nbytes)))
+
+
+# ---- oracle/_ref: the reference sources compiled here --------------------------------------------
+
+def ref_available(nverts: int) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libbarbu_ref_glsl_N{nverts}.so"))
+
+
+_ref_cache = {}
+
+
+def _ref(kind: str, nverts: int) -> C.CDLL:
+    key = (kind, nverts)
+    if key not in _ref_cache:
+        lib = C.CDLL(os.path.join(REF_DIR, f"libbarbu_ref_{kind}_N{nverts}.so"))
+        if kind == "host":
+            lib.ref_host_patch_indices.restype = C.c_int64
+            lib.ref_host_simplex2.restype = C.c_float
+            lib.ref_host_simplex2.argtypes = [C.c_float, C.c_float]
+        _ref_cache[key] = lib
+    return _ref_cache[key]
+
+
+def ref_update(pos4, vel4, nstrands: int, nverts: int, dt: float, scale: float, sphere):
+    """One Hair::update of the reference shader source (READ -> dispatch -> swap), in place."""
+    _ref("glsl", nverts).ref_glsl_update(_p(pos4), _p(vel4), C.c_int64(nstrands), C.c_float(dt), C.c_float(scale),
+                                         (C.c_float * 4)(*sphere))
+
+
+def ref_init_simulation(root_pos3, root_nrm3, seed: int, nverts: int, maxlength: float = 0.5):
+    S = root_pos3.shape[0]
+    planes = [np.empty((S * nverts, 4), np.float32) for _ in range(3)]
+    _ref("host", nverts).ref_host_init_simulation(_p(np.ascontiguousarray(root_pos3, np.float32)),
+                                                  _p(np.ascontiguousarray(root_nrm3, np.float32)), C.c_int64(S),
+                                                  C.c_uint(seed), C.c_float(maxlength), *[_p(a) for a in planes])
+    return tuple(planes)
+
+
+def ref_patch_indices(tri, nstrands: int, nverts: int) -> np.ndarray:
+    tri = np.ascontiguousarray(tri, np.int32).reshape(-1, 3)
+    out = np.empty(6 * tri.shape[0] * max(nverts - 1, 0), np.int32)
+    n = _ref("host", nverts).ref_host_patch_indices(_p(tri), C.c_int64(tri.shape[0]), C.c_int64(nstrands), _p(out))
+    assert n == out.size
+    return out
+
+
+def ref_simplex2(x: float, y: float) -> float:
+    return float(_ref("host", 4).ref_host_simplex2(x, y))

@@ -1,0 +1,302 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the golden
+fixtures. Exact profile: BIT-EXACT. Fast profile: <= 1e-5 relative per vertex after one step on
+well-conditioned states (BASELINE.json north_star; SURVEY.md App. B for what "well-conditioned" means).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import barbu_b200 as bb
+from oracle import pyoracle as po
+from tests.util import DT, SPHERE, assert_bit_equal, golden, ragged_state, rel_err, sphere_state
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = ["hair_N2_s100", "hair_N3_s145", "hair_N4_s145", "hair_N8_s145", "hair_N16_s100", "hair_N32_s100",
+                "hair_N32_s145", "hair_N64_s100"]
+
+
+def gpu_steps(pos, vel, S, N, nsteps, dt=DT, substeps=1, **cfg):
+    with bb.HairSim(S, N) as sim:
+        sim.configure(**cfg)
+        sim.upload(pos, vel)
+        for _ in range(nsteps):
+            sim.step(float(dt), substeps)
+        p, v, _ = sim.download()
+    return p, v
+
+
+# ---- against what the reference sources compute (golden fixtures) ---------------------------------
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_step_bit_exact_vs_reference_golden(name):
+    g = golden(name)
+    N, S = int(g["nverts"]), g["root_pos"].shape[0]
+    cfg = dict(scale=float(g["scale"]), sphere=tuple(g["sphere"]))
+    p1, v1 = gpu_steps(g["pos0"], g["vel0"], S, N, 1, g["dt"], **cfg)
+    assert_bit_equal(p1, g["pos1"], "pos after 1 update")
+    assert_bit_equal(v1, g["vel1"], "vel after 1 update")
+    p10, v10 = gpu_steps(g["pos0"], g["vel0"], S, N, 10, g["dt"], **cfg)
+    assert_bit_equal(p10, g["pos10"], "pos after 10 updates")
+    assert_bit_equal(v10, g["vel10"], "vel after 10 updates")
+    pw, vw = gpu_steps(g["pos10"], g["vel10"], S, N, 1, g["dt"], **cfg)
+    assert_bit_equal(pw, g["posw1"], "pos, warm state + 1 update")
+    assert_bit_equal(vw, g["velw1"], "vel, warm state + 1 update")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_strand_generation_bit_exact_vs_reference_golden(name):
+    g = golden(name)
+    N, S = int(g["nverts"]), g["root_pos"].shape[0]
+    with bb.HairSim(S, N) as sim:
+        sim.init_strands(g["root_pos"], g["root_nrm"], bb.random_values(int(g["seed"]), 0, S), 0.5)
+        pos, vel, _ = sim.download()
+    assert_bit_equal(pos, g["pos0"], "generated positions")
+    assert_bit_equal(vel, g["vel0"], "generated velocities")
+    assert_bit_equal(bb.build_patch_indices(g["tri"], N), g["patch"], "patch indices")
+
+
+# ---- against the oracle on seeded inputs -----------------------------------------------------------
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 48, 64, 100, 128])
+@pytest.mark.parametrize("S", [1, 33, 1000])
+def test_step_bit_exact_ragged_shapes(S, N):
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.2, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(3):
+        po.step(rp, rv, S, N, par)
+    gp, gv = gpu_steps(pos, vel, S, N, 3, scale=1.2, sphere=SPHERE)
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+
+
+@pytest.mark.parametrize("N,scale", [(16, 1.45), (32, 1.45), (32, 1.0)])
+def test_config1_size_many_steps_bit_exact(N, scale):
+    """BASELINE config 1 shape (4,096 strands) over 60 steps from the cold state, contacts included."""
+    _, _, _, _, pos, vel = sphere_state(64, 64, N)
+    S = 4096
+    par = po.default_params(dt=float(DT), scale=scale, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(60):
+        po.step(rp, rv, S, N, par, nthreads=8)
+    gp, gv = gpu_steps(pos, vel, S, N, 60, scale=scale, sphere=SPHERE)
+    assert_bit_equal(gp, rp, "positions after 60 steps")
+    assert_bit_equal(gv, rv, "velocities after 60 steps")
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 5, 12])
+def test_generic_kernel_other_iteration_counts(iters):
+    S, N = 500, 12
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.1, sphere=SPHERE, iterations=iters)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(2):
+        po.step(rp, rv, S, N, par)
+    gp, gv = gpu_steps(pos, vel, S, N, 2, scale=1.1, sphere=SPHERE, iterations=iters)
+    assert_bit_equal(gp, rp)
+    assert_bit_equal(gv, rv)
+
+
+def test_substeps_equal_repeated_steps_with_dt_over_k():
+    S, N = 777, 32
+    pos, vel = ragged_state(S, N)
+    h = np.float32(DT) / np.float32(4)
+    par = po.default_params(dt=float(h), scale=1.0, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(8):
+        po.step(rp, rv, S, N, par)
+    gp, gv = gpu_steps(pos, vel, S, N, 2, DT, substeps=4, scale=1.0, sphere=SPHERE)
+    assert_bit_equal(gp, rp)
+    assert_bit_equal(gv, rv)
+
+
+def test_special_values_follow_reference_arithmetic():
+    """-0.0 roots, a vertex exactly on its predecessor (normalize(0) -> NaN) and a vertex at the sphere
+    centre must come out exactly as the reference arithmetic produces them (App. A note 2: not "fixed")."""
+    S, N = 64, 8
+    pos, vel = ragged_state(S, N)
+    pos[0 * N, :3] = (-0.0, 1.0, -0.0)
+    pos[1 * N + 3, :3] = pos[1 * N + 2, :3]
+    vel[1 * N + 3, :3] = vel[1 * N + 2, :3]
+    pos[2 * N + 5, :3] = (0.0, 0.0, 0.0)
+    par = po.default_params(dt=float(DT), scale=1.0, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    po.step(rp, rv, S, N, par)
+    gp, gv = gpu_steps(pos, vel, S, N, 1, scale=1.0, sphere=SPHERE)
+    assert_bit_equal(gp, rp)
+    assert_bit_equal(gv, rv)
+
+
+# ---- extensions (no reference implementation; parity is against the oracle's definition) -----------
+
+def test_extensions_wind_drag_capsules_bit_exact():
+    S, N = 600, 16
+    pos, vel = ragged_state(S, N)
+    caps = [((0.3, 0.2, 0.1), (-0.4, 0.5, 0.0), 0.35), ((0.0, -0.6, 0.2), (0.0, -0.6, 0.2), 0.5)]
+    par = po.default_params(dt=float(DT), scale=1.0, sphere=SPHERE, wind=(3.0, 0.5, -2.0), drag=0.05, ncapsules=len(caps))
+    gcfg = bb.default_params()
+    gcfg.scale, gcfg.drag, gcfg.ncapsules = 1.0, 0.05, len(caps)
+    for i, x in enumerate(SPHERE):
+        gcfg.sphere[i] = x
+    for i, x in enumerate((3.0, 0.5, -2.0)):
+        gcfg.wind[i] = x
+    for q, (a, b, r) in enumerate(caps):
+        for i in range(3):
+            par.capsules[q].a[i], par.capsules[q].b[i] = a[i], b[i]
+            gcfg.capsules[q].a[i], gcfg.capsules[q].b[i] = a[i], b[i]
+        par.capsules[q].radius = gcfg.capsules[q].radius = r
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(5):
+        po.step(rp, rv, S, N, par)
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        sim.upload(pos, vel)
+        for _ in range(5):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp)
+    assert_bit_equal(gv, rv)
+
+
+def test_dq_skinned_roots_bit_exact():
+    rng = np.random.default_rng(5)
+    S, N, J = 900, 8, 6
+    root_pos, root_nrm, _, rv, pos, vel = sphere_state(30, 30, N)
+    q = rng.standard_normal((J, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    dual = (rng.standard_normal((J, 4)) * 0.1).astype(np.float32)
+    dq = np.concatenate([q, dual], axis=1).astype(np.float32)
+    joints = rng.integers(0, J, (S, 4)).astype(np.int32)
+    w = rng.dirichlet(np.ones(4), S).astype(np.float32)[:, :3]
+    w[::7, 0] = 0.0                                   # exercises the weights.x <= eps early-out
+    exp_pos, _ = po.skin_roots_dq(root_pos, root_nrm, joints, w, dq)
+    with bb.HairSim(S, N) as sim:
+        sim.upload(pos, vel)
+        sim.set_skin(root_pos, joints, w)
+        sim.skin_roots(dq)
+        gp, _, _ = sim.download()
+    expect = pos.copy()
+    expect[::N, :3] = exp_pos
+    assert_bit_equal(gp, expect, "skinned roots")
+
+
+# ---- fast profile: tolerance ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_fast_profile_within_1e5_after_one_step(N):
+    """Tolerance of BASELINE.json north_star: <= 1e-5 relative per vertex after one step.
+    States: cold with scale 1.0, and warm (after 60 exact steps) with the reference's 1.45."""
+    TOL = 1e-5
+    S = 4096
+    _, _, _, _, pos, vel = sphere_state(64, 64, N)
+    par = po.default_params(dt=float(DT), scale=1.0, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    po.step(rp, rv, S, N, par, nthreads=8)
+    gp, gv = gpu_steps(pos, vel, S, N, 1, scale=1.0, sphere=SPHERE, math=bb.BH_MATH_FAST)
+    assert rel_err(gp, rp).max() <= TOL
+    # warm state
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE)
+    wp, wv = pos.copy(), vel.copy()
+    for _ in range(60):
+        po.step(wp, wv, S, N, par, nthreads=8)
+    rp, rv = wp.copy(), wv.copy()
+    po.step(rp, rv, S, N, par, nthreads=8)
+    gp, gv = gpu_steps(wp, wv, S, N, 1, scale=1.45, sphere=SPHERE, math=bb.BH_MATH_FAST)
+    err = rel_err(gp, rp)
+    # contact bifurcations (a vertex within rounding of the sphere surface) are excluded by quantile, and reported
+    assert np.quantile(err, 0.999) <= TOL, f"p99.9 {np.quantile(err, 0.999):.3e} max {err.max():.3e}"
+    # velocities are cancellation differences: absolute tolerance scaled by segment length (App. B iv)
+    seg = 1.45 * np.maximum(rp[:, 3], 1e-3)
+    assert np.quantile(np.abs(gv[:, :3] - rv[:, :3]).max(axis=1) / seg, 0.999) <= 1e-4
+
+
+# ---- generators, host path, API behaviour ---------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols,N", [(8, 16, 4), (64, 64, 16), (33, 17, 5)])
+def test_sphere_scalp_generation_bit_exact_and_sharded(rows, cols, N):
+    S = rows * cols
+    _, _, tri, rv, pos, vel = sphere_state(rows, cols, N)
+    assert_bit_equal(bb.random_values(1234, 0, S), rv, "rand() jitter")
+    assert_bit_equal(bb.sphere_scalp_triangles(rows, cols), tri, "scalp triangles")
+    with bb.HairSim(S, N) as sim:
+        sim.init_sphere_scalp(rows, cols, 0, rv)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, pos)
+    assert_bit_equal(gv, vel)
+    # two shards, as two ranks would hold them
+    first = S // 2 + 3
+    for lo, hi in ((0, first), (first, S)):
+        with bb.HairSim(hi - lo, N) as sim:
+            sim.init_sphere_scalp(rows, cols, lo, bb.random_values(1234, lo, hi - lo))
+            gp, _, _ = sim.download()
+        assert_bit_equal(gp, pos[lo * N:hi * N], f"shard [{lo},{hi})")
+    assert_bit_equal(bb.build_patch_indices(tri, N), po.patch_indices(tri, N), "patch indices")
+
+
+def test_step_host_equals_device_resident_step():
+    S, N = 20000, 16
+    pos, vel = ragged_state(S, N)
+    gp, gv = gpu_steps(pos, vel, S, N, 1, DT, substeps=4, scale=1.0, sphere=SPHERE)
+    hp, hv = bb.PinnedBuffer(4 * S * N), bb.PinnedBuffer(4 * S * N)
+    hp.array[:] = pos.reshape(-1)
+    hv.array[:] = vel.reshape(-1)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.0, sphere=SPHERE)
+        sim.step_host(float(DT), 4, hp.array, hv.array)
+        assert sim.launch_count >= 4
+    assert_bit_equal(hp.array.reshape(-1, 4), gp)
+    assert_bit_equal(hv.array.reshape(-1, 4), gv)
+    hp.free(); hv.free()
+
+
+def test_api_error_behaviour():
+    lib = bb.load_library()
+    with bb.HairSim(10, 4) as sim:
+        with pytest.raises(bb.BarbuHairError) as e:
+            sim.step(0.01, 1)                       # no state yet: Hair::update before setup
+        assert e.value.code == 3
+        with pytest.raises(bb.BarbuHairError):
+            sim.configure(iterations=-1)
+        with pytest.raises(bb.BarbuHairError):
+            sim.configure(math=7)
+        with pytest.raises(bb.BarbuHairError):
+            sim.register_gl_buffer(1)               # no GL context in this process
+        assert b"GL" in lib.bh_last_error() or len(lib.bh_last_error()) > 0
+    h = C.c_void_p()
+    assert lib.bh_create(C.byref(h), 0, 4, 0) == 1
+    assert lib.bh_create(C.byref(h), 4, 4, 99) == 1
+    with pytest.raises(bb.BarbuHairError) as e:
+        bb.build_patch_indices(np.array([[0, 1, 2 ** 30]], np.int32), 4)
+    assert e.value.code == 5
+
+
+def test_hair_module_mirror():
+    """The Hair-shaped adaptor: setup / set_bounding_sphere / update as Renderer::update drives them
+    (core/renderer.cc:69-81), against the oracle."""
+    rows, cols, N = 16, 28, 4                        # 448 strands x 4 CPs: the reference's default workload size
+    root_pos, root_nrm, tri, rv, pos, vel = sphere_state(rows, cols, N)
+    hair = bb.Hair(params=bb.Hair.Parameters(ncontrol_points=N))
+    hair.init()
+    hair.update(float(DT))
+    assert not hair.initialized() and "without initialization" in hair.log[-1]
+    hair.setup(None)
+    assert not hair.initialized() and "not found" in hair.log[-1]
+    hair.set_bounding_sphere(SPHERE)
+    hair.setup(bb.ScalpMesh(root_pos, root_nrm, tri))
+    assert hair.initialized() and hair.nroots == 448
+    gp, gv, gt = hair.sim.download(tan=True)
+    assert_bit_equal(gp, pos)
+    assert_bit_equal(gt, po.init_tangents(root_nrm, N), "tangent plane")
+    assert_bit_equal(hair.patch_indices, po.patch_indices(tri, N))
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE)
+    for _ in range(4):
+        hair.update(float(DT))
+        po.step(pos, vel, 448, N, par)
+    gp, gv, gt2 = hair.sim.download(tan=True)
+    assert_bit_equal(gp, pos)
+    assert_bit_equal(gv, vel)
+    assert_bit_equal(gt2, gt, "tangent plane untouched by the simulation")
+    hair.deinit()
+    assert not hair.initialized()
