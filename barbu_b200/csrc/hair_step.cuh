@@ -31,7 +31,7 @@ struct StepArgs {
 // math: 0 exact, 1 fast. Returns the CUDA error of the launch.
 cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream);
 
-// Which kernel launch_step picks for (nverts, iterations, ncaps): 0 = pipelined, 1 = generic.
+// Which kernel launch_step picks: 0 = pipelined, 1 = generic.
 int step_kernel_kind(int nverts, int iterations, int ncaps);
 
 }  // namespace bh
