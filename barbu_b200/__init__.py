@@ -5,8 +5,8 @@ include/barbu_hair.h), the build recipe, and the host-side mirror of the referen
 """
 from .hair import (BH_MATH_EXACT, BH_MATH_FAST, BarbuHairError, BhParams, Hair, HairSim, PinnedBuffer, ScalpMesh,
                    build_patch_indices, default_params, init_tangents_host, load_library, random_values,
-                   sphere_scalp_triangles)
+                   selftest_math, sphere_scalp_triangles)
 
 __all__ = ["BH_MATH_EXACT", "BH_MATH_FAST", "BarbuHairError", "BhParams", "Hair", "HairSim", "PinnedBuffer",
            "ScalpMesh", "build_patch_indices", "default_params", "init_tangents_host", "load_library",
-           "random_values", "sphere_scalp_triangles"]
+           "random_values", "selftest_math", "sphere_scalp_triangles"]

@@ -57,6 +57,7 @@ struct bh_sim {
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
   int64_t launches = 0;
+  unsigned int* tile_counters = nullptr;  // kHostPipeStreams + 1 words: one tile scheduler per stream that may be in flight
   // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)
   float* root_pos3 = nullptr;
   float* root_nrm3 = nullptr;
@@ -160,6 +161,7 @@ int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
   s->device = device; s->nstrands = nstrands; s->nverts = nverts; s->nvertices = nstrands * (int64_t)nverts;
   bh_default_params(&s->params);
   cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&s->tile_counters, sizeof(unsigned int) * 32 * (kHostPipeStreams + 1));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
   for (int i = 0; i < kHostPipeStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
   if (e != cudaSuccess) { (void)cudaGetLastError(); bh_destroy(s); return fail(BH_ERR_CUDA, "bh_create: allocation", e); }
@@ -173,7 +175,7 @@ int bh_destroy(bh_sim* s) {
   if (!s) return BH_OK;
   DeviceGuard g(s->device);
   if (s->gl_resource) cudaGraphicsUnregisterResource(s->gl_resource);
-  cudaFree(s->buffer0); cudaFree(s->root_pos3); cudaFree(s->root_nrm3);
+  cudaFree(s->buffer0); cudaFree(s->tile_counters); cudaFree(s->root_pos3); cudaFree(s->root_nrm3);
   cudaFree(s->skin_rest3); cudaFree(s->skin_joints4); cudaFree(s->skin_weights3); cudaFree(s->skin_dq);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
@@ -358,7 +360,7 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   const bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
   for (int q = 0; q < substeps; ++q) {
-    BH_CUDA(bh::launch_step(a, s->params.math, s->stream));
+    BH_CUDA(bh::launch_step(a, s->params.math, s->stream, s->tile_counters + 32 * kHostPipeStreams));
     s->launches += 1;
   }
   return unmap_gl(s);
@@ -393,7 +395,7 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
     e = cudaMemcpyAsync(dP, pos4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dV, vel4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
     const bh::StepArgs a = make_args(s, h, dP, dV, count);
-    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, st); s->launches += 1; }
+    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, st, s->tile_counters + 32 * (k % kHostPipeStreams)); s->launches += 1; }
     if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(vel4 + 4 * off, dV, bytes, cudaMemcpyDeviceToHost, st);
   }
@@ -415,6 +417,23 @@ int bh_host_free(void* ptr) {
 }
 
 int64_t bh_launch_count(const bh_sim* s) { return s ? s->launches : 0; }
+
+int bh_step_kernel_kind(const bh_sim* s) {
+  if (!s) return -1;
+  return bh::step_kernel_kind(make_args(s, 0.0f, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands));
+}
+
+int bh_selftest_math(int device, uint64_t* mismatches) {
+  if (!mismatches) return fail(BH_ERR_INVALID, "bh_selftest_math: NULL argument");
+  int ndev = 0;
+  BH_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BH_ERR_INVALID, "bh_selftest_math: no such CUDA device");
+  DeviceGuard g(device);
+  unsigned long long bad = 0;
+  BH_CUDA(bh::selftest_inversesqrt(&bad));
+  *mismatches = bad;
+  return BH_OK;
+}
 
 int bh_set_skin(bh_sim* s, const float* rest_root_pos3, const int32_t* joints4, const float* weights3) {
   if (!s || !rest_root_pos3 || !joints4 || !weights3) return fail(BH_ERR_INVALID, "bh_set_skin: NULL argument");

@@ -461,10 +461,14 @@ cudaError_t launch_t(const StepArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-// 0 = pipelined kernel, 1 = generic kernel (iteration count != 8)
-int step_kernel_kind(int /*nverts*/, int iterations, int /*ncaps*/) { return iterations == kChunk ? 0 : 1; }
+int step_kernel_kind(const StepArgs& a) {
+  if (stream_kernel_eligible(a)) return 0;
+  return a.iterations == kChunk && a.r2 <= 1.8446744073709551616e19f ? 1 : 2;
+}
 
-cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream) {
+cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
+  if (a.nstrands <= 0 || a.nverts <= 0) return cudaSuccess;
+  if (tile_counter && stream_kernel_eligible(a)) return launch_step_stream(a, math, stream, tile_counter);
   const bool caps = a.ncaps > 0;
   if (math == 0) return caps ? launch_t<MathExact, true>(a, stream) : launch_t<MathExact, false>(a, stream);
   return caps ? launch_t<MathFast, true>(a, stream) : launch_t<MathFast, false>(a, stream);

@@ -28,10 +28,16 @@ struct StepArgs {
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.
-// math: 0 exact, 1 fast. Returns the CUDA error of the launch.
-cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream);
+// math: 0 exact, 1 fast. `tile_counter`: 4 bytes of device scratch owned by the caller and not shared with
+// any launch that may run concurrently (the streaming kernel's tile scheduler). Returns the CUDA error.
+cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 
-// Which kernel launch_step picks: 0 = pipelined, 1 = generic.
-int step_kernel_kind(int nverts, int iterations, int ncaps);
+// Which kernel launch_step picks: 0 = streaming (hair_stream.cu), 1 = per-strand pipelined, 2 = generic.
+int step_kernel_kind(const StepArgs& a);
+
+// hair_stream.cu
+bool stream_kernel_eligible(const StepArgs& a);
+cudaError_t selftest_inversesqrt(unsigned long long* mismatches);
+cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 
 }  // namespace bh

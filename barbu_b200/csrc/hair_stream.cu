@@ -1,0 +1,525 @@
+// hair_stream.cu — the streaming step kernel for sm_100a (the hot path at nverts % 8 == 0).
+//
+// Same arithmetic as hair_step.cu (one dispatch of cs_simulation.glsl:170-208 + PingPongBuffer::swap,
+// written back in place), organised for Blackwell:
+//
+//  * TMA tiles. A warp owns TILES of 32 consecutive strands. A tile moves between HBM and shared memory
+//    in chunks of 8 vertices: one cp.async.bulk.tensor.2d box of 32 rows x 128 B per plane, written
+//    with the 128-byte swizzle, so that lane l finds vertex j of ITS strand at 16-byte column
+//    j ^ (l & 7) of row l — conflict-free LDS.128/STS.128 with no transposing copy loop. Two chunk
+//    buffers per warp form a ring on two mbarriers; a finished chunk leaves through a TMA tile store
+//    from the same buffer (the result of vertex t-8 is written into the slot vertex t was read from).
+//  * Persistent warps. The grid is (#SMs x resident blocks); every warp pulls tiles from an atomic
+//    counter and runs ONE software pipeline across all of them: at step t stage k applies constraint
+//    iteration k+1 to stream vertex t-k. A strand root entering the stream passes through the stages
+//    unchanged and resets their "previous vertex", so the 8-step fill/drain is paid once per warp
+//    instead of once per strand, and every step of the launch is the same steady-state body.
+//  * Packed FP32x2. The eight stage chains of a thread are mutually independent, so stages (a, a+4)
+//    share one 64-bit register pair per coordinate and every FADD/FMUL/FFMA of the projection and of
+//    the collision test issues as FADD2/FMUL2/FFMA2 — half the issue slots at the same FP32 lane
+//    throughput (measured: tools/ubench/f32x2.cu). Packed add/mul/fma round exactly like the scalar
+//    .rn forms; in the exact profile a product is written fma(a, b, -0.0) with the -0.0 taken from a
+//    kernel parameter, because ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even with
+//    explicit rounding modifiers and --fmad=false.
+//
+// Algorithmic traffic: 16 B pos + 16 B vel read and the same written = 64 B per vertex per launch.
+#include "hair_step.cuh"
+#include "hair_math.cuh"
+
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+
+namespace bh {
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int kK = 8;                            // constraint iterations == pipeline depth == vertices per chunk
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kPlaneTile = 32 * 128;             // bytes of one plane of one chunk: 32 strands x 8 vertices x 16 B
+constexpr int kStageBytes = 2 * kPlaneTile;      // position + velocity
+constexpr int kWarpTileBytes = 2 * kStageBytes;  // two stages
+constexpr int kRingBytes = kK * 32 * 4;          // rest lengths of the 8 vertices in flight, [slot][lane]
+constexpr int kSmemBytes = 1024 /* alignment slack */ + kWarps * (kWarpTileBytes + kRingBytes) + kWarps * 2 * 8;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BH_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BH_DONE;\n"
+      "bra BH_WAIT;\n"
+      "BH_DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- packed pairs ------------------------------------------------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ float lo(u64 v) { float l, h; asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(v)); (void)h; return l; }
+__device__ __forceinline__ float hi(u64 v) { float l, h; asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(v)); (void)l; return h; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2_contractable(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ float rsq_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+constexpr u64 kOne2 = 0x3f8000003f800000ull;
+constexpr u64 kHalf2 = 0x3f0000003f000000ull;
+
+struct V3p { u64 x, y, z; };                     // lo half: stage a, hi half: stage a + 4
+
+// Packed counterparts of MathExact / MathFast (hair_math.cuh). `nz` is (-0.0f, -0.0f) from a kernel parameter.
+struct PackedExact {
+  typedef MathExact S;
+  static constexpr bool kRangeChecked = true;
+  static __device__ __forceinline__ u64 mul(u64 a, u64 b, u64 nz) { return fma2(a, b, nz); }   // RN(a*b + -0) == RN(a*b), sign of zero included
+  static __device__ __forceinline__ u64 dot(V3p a, V3p b, u64 nz) { return add2(add2(mul(a.x, b.x, nz), mul(a.y, b.y, nz)), mul(a.z, b.z, nz)); }
+  // -(1 / sqrt(x)) for both halves, x in [2^-64, 2^64): the sequence of MathExact::inversesqrt_in_range, with the
+  // reciprocal seeded by rcp(-s) so that no packed negation is needed afterwards (RN is sign-symmetric).
+  static __device__ __forceinline__ u64 neg_inversesqrt_in_range(u64 x, u64 nz) {
+    const u64 y = pk(rsq_approx(lo(x)), rsq_approx(hi(x)));
+    const u64 s0 = mul(x, y, nz);
+    const u64 h = mul(y, kHalf2, nz);
+    const u64 s = fma2(fma2(neg2(s0), s0, x), h, s0);                       // sqrt_rn(x)
+    const u64 rn = pk(rcp_approx(-lo(s)), rcp_approx(-hi(s)));              // -r
+    return fma2(rn, fma2(rn, s, kOne2), rn);                                // -(r + r*(1 - r*s)) = -rcp_rn(s)
+  }
+  static __device__ __forceinline__ u64 neg_inversesqrt_ieee(u64 x) {
+    return pk(-__frcp_rn(__fsqrt_rn(lo(x))), -__frcp_rn(__fsqrt_rn(hi(x))));
+  }
+  static __device__ __forceinline__ float inv_of(float ninv) { return -ninv; }
+  // p0 + L * (vd * inv) given ninv = -inv:  p0 - L * (vd * ninv), bit-identical
+  static __device__ __forceinline__ V3p project(V3p p0, V3p vd, u64 ninv, u64 L, u64 nz) {
+    return { sub2(p0.x, mul(L, mul(vd.x, ninv, nz), nz)), sub2(p0.y, mul(L, mul(vd.y, ninv, nz), nz)), sub2(p0.z, mul(L, mul(vd.z, ninv, nz), nz)) };
+  }
+  // c + r * (pt * inv) given ninv
+  static __device__ __forceinline__ V3p push_out(V3p c, V3p pt, u64 ninv, u64 r, u64 nz) {
+    return { sub2(c.x, mul(r, mul(pt.x, ninv, nz), nz)), sub2(c.y, mul(r, mul(pt.y, ninv, nz), nz)), sub2(c.z, mul(r, mul(pt.z, ninv, nz), nz)) };
+  }
+};
+
+struct PackedFast {
+  typedef MathFast S;
+  static constexpr bool kRangeChecked = false;
+  static __device__ __forceinline__ u64 mul(u64 a, u64 b, u64) { return mul2_contractable(a, b); }
+  static __device__ __forceinline__ u64 dot(V3p a, V3p b, u64) { return fma2(a.z, b.z, fma2(a.y, b.y, mul2_contractable(a.x, b.x))); }
+  // this profile keeps the inverse square root with its own sign (one MUFU.RSQ per half)
+  static __device__ __forceinline__ u64 neg_inversesqrt_in_range(u64 x, u64) { return pk(rsq_approx(lo(x)), rsq_approx(hi(x))); }
+  static __device__ __forceinline__ u64 neg_inversesqrt_ieee(u64 x) { return neg_inversesqrt_in_range(x, 0); }
+  static __device__ __forceinline__ float inv_of(float isq) { return isq; }
+  static __device__ __forceinline__ V3p project(V3p p0, V3p vd, u64 isq, u64 L, u64) {
+    const u64 s = mul2_contractable(L, isq);                                // L * inv
+    return { fma2(vd.x, s, p0.x), fma2(vd.y, s, p0.y), fma2(vd.z, s, p0.z) };
+  }
+  static __device__ __forceinline__ V3p push_out(V3p c, V3p pt, u64 isq, u64 r, u64) {
+    const u64 s = mul2_contractable(r, isq);
+    return { fma2(pt.x, s, c.x), fma2(pt.y, s, c.y), fma2(pt.z, s, c.z) };
+  }
+};
+
+__device__ __forceinline__ V3p sub3(V3p a, V3p b) { return { sub2(a.x, b.x), sub2(a.y, b.y), sub2(a.z, b.z) }; }
+__device__ __forceinline__ V3 lo3(V3p v) { return { lo(v.x), lo(v.y), lo(v.z) }; }
+__device__ __forceinline__ V3 hi3(V3p v) { return { hi(v.x), hi(v.y), hi(v.z) }; }
+__device__ __forceinline__ V3p pk3(V3 l, V3 h) { return { pk(l.x, h.x), pk(l.y, h.y), pk(l.z, h.z) }; }
+
+// vec3(mat4(1.0) * vec4(p, 1.0)) in GLM's operation order (see root_transform in hair_step.cu).
+template <class M>
+__device__ __forceinline__ V3 root_transform(V3 p) {
+  const float zx = M::mul(0.0f, p.x), zy = M::mul(0.0f, p.y), zz = M::mul(0.0f, p.z);
+  const float z1 = M::mul(0.0f, 1.0f);
+  return { M::add(M::add(M::mul(1.0f, p.x), zy), M::add(zz, z1)),
+           M::add(M::add(zx, M::mul(1.0f, p.y)), M::add(zz, z1)),
+           M::add(M::add(zx, zy), M::add(M::mul(1.0f, p.z), z1)) };
+}
+
+// Pipeline registers. Pair a holds stages a (lo) and a + 4 (hi).
+struct Pipe {
+  V3p X[4];        // D(i-1, k+1): the already projected previous vertex of each stage
+  V3p P[4];        // C(i, k): input of each stage
+  u64 L[4];        // sf * rest_i of the vertex in each stage
+  V3 heldD, heldd; // D(i, 8) and d_i of the vertex waiting for d_{i+1}
+  V3 rootV;        // velocity written for the root that entered last
+};
+
+template <class PM> __device__ __noinline__ u64 neg_inversesqrt_slow(u64 x) { return PM::neg_inversesqrt_ieee(x); }
+
+// ninv[a] = -inversesqrt(x[a]); the (rare) IEEE-builtin path is taken by the whole warp or not at all.
+template <class PM>
+__device__ __forceinline__ void neg_inversesqrt_batch(const u64 (&x)[4], u64 (&ninv)[4], bool ok, u64 nz) {
+  if (!PM::kRangeChecked || __all_sync(0xffffffffu, ok)) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ninv[a] = PM::neg_inversesqrt_in_range(x[a], nz);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ninv[a] = neg_inversesqrt_slow<PM>(x[a]);
+  }
+}
+
+__device__ __forceinline__ float min8(const u64 (&v)[4]) {
+  return fminf(fminf(fminf(lo(v[0]), hi(v[0])), fminf(lo(v[1]), hi(v[1]))), fminf(fminf(lo(v[2]), hi(v[2])), fminf(lo(v[3]), hi(v[3]))));
+}
+__device__ __forceinline__ float max8(const u64 (&v)[4]) {
+  return fmaxf(fmaxf(fmaxf(lo(v[0]), hi(v[0])), fmaxf(lo(v[1]), hi(v[1]))), fmaxf(fmaxf(lo(v[2]), hi(v[2])), fmaxf(lo(v[3]), hi(v[3]))));
+}
+
+// One step of the stream pipeline: slot j of the current chunk.
+//   ROOT : this chunk starts a strand (vertex 0 is in slot 0), so at step j stage j holds a root, and step 7 finalises
+//          the tip of the previous strand.
+//   fin_root (runtime, warp-uniform): the vertex finalised by this step is a root.
+template <class PM, bool ORIGIN, bool ROOT>
+__device__ __forceinline__ void stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
+                                            float4* slotP, float4* slotV, float* slotR) {
+  typedef typename PM::S M;
+  const float rest_out = *slotR;
+  const V3 rootV_out = s.rootV;
+  {
+    const float4 Pin = *slotP, Vin = *slotV;
+    *slotR = Pin.w;
+    V3 x;
+    if (ROOT && j == 0) {
+      x = root_transform<M>(V3{ Pin.x, Pin.y, Pin.z });
+      s.rootV = vsub<M>(x, V3{ Pin.x, Pin.y, Pin.z });                      // p.velocity = p.position - lastPosition (cs:192)
+    } else {
+      float4 V = Vin;
+      if (a.use_drag) { V.x = M::mul(V.x, a.keep); V.y = M::mul(V.y, a.keep); V.z = M::mul(V.z, a.keep); }
+      x = { __fmaf_rn(a.dt2, a.fx, __fmaf_rn(a.dt, V.x, Pin.x)), __fmaf_rn(a.dt2, a.fy, __fmaf_rn(a.dt, V.y, Pin.y)),
+            __fmaf_rn(a.dt2, a.fz, __fmaf_rn(a.dt, V.z, Pin.z)) };         // cs:181-182
+    }
+    s.P[0] = pk3(x, hi3(s.P[0]));
+    s.L[0] = pk(M::mul(a.sf, Pin.w), hi(s.L[0]));
+  }
+  // ---- phase A: the eight projections, as four packed chains ---------------------------------------
+  V3p vd[4], D[4];
+  u64 dp[4], ninv[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    vd[q] = sub3(s.P[q], s.X[q]);
+    dp[q] = PM::dot(vd[q], vd[q], nz);
+  }
+  bool ok = true;
+  if (PM::kRangeChecked) ok = M::in_fast_range(min8(dp)) && M::in_fast_range(max8(dp));   // NaN stays NaN on both paths
+  neg_inversesqrt_batch<PM>(dp, ninv, ok, nz);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) D[q] = PM::project(s.X[q], vd[q], ninv[q], s.L[q], nz);
+  if (ROOT) {                                                               // the root passes through: D(0, k) = X[0]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j == q) D[q] = pk3(lo3(s.P[q]), hi3(D[q]));
+      if (j == q + 4) D[q] = pk3(lo3(D[q]), hi3(s.P[q]));
+    }
+  }
+  const V3 D7 = hi3(D[3]);
+  const V3 dF = vsub<M>(D7, hi3(s.P[3]));                                   // s_particles[i].velocity = p1_bis - p1 (cs:116)
+  V3 fp = s.heldD;                                                          // the vertex being finalised: t-8
+  V3 fw = M::scale(dF, a.damp);                                             // cs:119-121
+  if (ROOT && j == 7) fw = s.heldd;                                         // the tip keeps its own d
+
+  // ---- phase T: collision tests; the hi half of pair 3 is the finalised vertex (stage 7 is tested next step) ----
+  const V3p c2 = { pk(a.cx, a.cx), pk(a.cy, a.cy), pk(a.cz, a.cz) };
+  V3p T[4], pt[4];
+  u64 dpc[4];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) T[q] = D[q];
+  T[3] = pk3(lo3(D[3]), fp);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    pt[q] = ORIGIN ? T[q] : sub3(T[q], c2);
+    dpc[q] = PM::dot(pt[q], pt[q], nz);
+  }
+  if (ROOT) {                                                               // roots do not collide (cs:149-151: index > 0)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j == q) dpc[q] = pk(__int_as_float(0x7f800000), hi(dpc[q]));
+      if (q < 3 && j == q + 4) dpc[q] = pk(lo(dpc[q]), __int_as_float(0x7f800000));
+    }
+  }
+  const float mnc = min8(dpc);
+
+  // ---- phase B: push-outs, only when some lane of the warp touches the sphere --------------------
+  V3p C[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) C[q] = T[q];
+  if (__any_sync(0xffffffffu, mnc < a.r2)) {
+    // a hit has dpc < r2 <= 2^64 (launcher guarantees), so only the lower bound of the fast range can fail
+    u64 ninvc[4];
+    neg_inversesqrt_batch<PM>(dpc, ninvc, !(mnc < 5.42101086242752217e-20f), nz);
+    const u64 r2p = pk(a.r, a.r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const V3p Q = PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
+      const bool hl = lo(dpc[q]) < a.r2, hh = hi(dpc[q]) < a.r2;
+      C[q].x = pk(hl ? lo(Q.x) : lo(T[q].x), hh ? hi(Q.x) : hi(T[q].x));
+      C[q].y = pk(hl ? lo(Q.y) : lo(T[q].y), hh ? hi(Q.y) : hi(T[q].y));
+      C[q].z = pk(hl ? lo(Q.z) : lo(T[q].z), hh ? hi(Q.z) : hi(T[q].z));
+    }
+    if (hi(dpc[3]) < a.r2) {                                                // the finalised vertex: vel = reflect(vel, n)
+      const float inv = PM::inv_of(hi(ninvc[3]));
+      const V3 n = M::scale(hi3(pt[3]), inv);
+      fw = M::reflect(fw, n);
+    }
+  }
+  fp = hi3(C[3]);
+
+  // ---- commit ------------------------------------------------------------------------------------
+  float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out), oV = make_float4(fw.x, fw.y, fw.z, 0.f);
+  if (fin_root) {                                                           // root: position as transformed, no collision
+    oP = make_float4(s.heldD.x, s.heldD.y, s.heldD.z, rest_out);
+    oV = make_float4(rootV_out.x, rootV_out.y, rootV_out.z, 0.f);
+  }
+  *slotP = oP;
+  *slotV = oV;
+  s.heldD = D7; s.heldd = dF;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s.X[q] = D[q];
+  // vertex moves to the next stage: pair q -> pair q+1; stage 3 -> stage 4 (lo of pair 3 -> hi of pair 0)
+  const V3 c3 = lo3(C[3]);
+  const float l3 = lo(s.L[3]);
+#pragma unroll
+  for (int q = 3; q >= 1; --q) { s.P[q] = C[q - 1]; s.L[q] = s.L[q - 1]; }
+  s.P[0] = pk3(V3{ 0.f, 0.f, 0.f }, c3);
+  s.L[0] = pk(0.f, l3);
+}
+
+template <class PM, bool ORIGIN>
+__global__ void __launch_bounds__(kThreads, 3)
+hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap mapP,
+                        const __grid_constant__ CUtensorMap mapV, unsigned int* __restrict__ tile_counter, const u64 nz) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // 128B-swizzled tiles repeat every 1024 B
+  unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+  unsigned char* tiles = gen + warp * kWarpTileBytes;                       // [stage][plane][32 x 128 B]
+  float* ring = reinterpret_cast<float*>(gen + kWarps * kWarpTileBytes + warp * kRingBytes);
+  const uint32_t tiles_s = base + warp * kWarpTileBytes;
+  const uint32_t bar_s = base + kWarps * (kWarpTileBytes + kRingBytes) + warp * 16;
+
+  const int chunks = a.nverts / kK;                                         // per strand
+  const unsigned int ntiles = (unsigned int)((a.nstrands + 31) / 32);
+
+  if (lane == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  auto grab = [&]() -> int {                                                // next tile of this warp, -1 when none is left
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(tile_counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return t < ntiles ? (int)t : -1;
+  };
+  auto issue_load = [&](int tile, int c, int b) {                           // lane 0 only
+    const uint32_t bar = bar_s + 8 * b, dst = tiles_s + b * kStageBytes;
+    mbar_expect_tx(bar, kStageBytes);
+    tma_load_tile(dst, &mapP, c * 32, tile * 32, bar);
+    tma_load_tile(dst + kPlaneTile, &mapV, c * 32, tile * 32, bar);
+  };
+  auto issue_store = [&](int tile, int c, int b) {                          // lane 0 only
+    const uint32_t src = tiles_s + b * kStageBytes;
+    tma_store_tile(&mapP, c * 32, tile * 32, src);
+    tma_store_tile(&mapV, c * 32, tile * 32, src + kPlaneTile);
+    tma_commit();
+  };
+
+  // chunk positions: S = being stored (q-1), C = being computed (q), N = loaded (q+1), L = next to load (q+2)
+  int tC = grab(), cC = 0;
+  if (tC < 0) return;
+  auto next_pos = [&](int& t, int& c) {
+    if (t < 0) return;
+    if (++c == chunks) { c = 0; t = grab(); }
+  };
+  int tN = tC, cN = cC; next_pos(tN, cN);
+  int tL = tN, cL = cN; next_pos(tL, cL);
+  if (lane == 0) {
+    issue_load(tC, cC, 0);
+    if (tN >= 0) issue_load(tN, cN, 1);
+  }
+  int tS = -1, cS = 0;
+
+  Pipe s;
+  {
+    // benign fill values: far from any collider, non-degenerate segments, zero length
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const u64 x = pk(1.0e3f + 10.f * q, 1.0e3f + 10.f * (q + 4)), p = pk(1.0e3f + 10.f * q + 10.f, 1.0e3f + 10.f * (q + 4) + 10.f);
+      s.X[q] = { x, x, x }; s.P[q] = { p, p, p }; s.L[q] = 0ull;
+    }
+    s.heldD = { 1.0e3f, 1.0e3f, 1.0e3f };
+    s.heldd = s.rootV = { 0.f, 0.f, 0.f };
+  }
+  for (int j = 0; j < kK; ++j) ring[j * 32 + lane] = 0.f;
+
+  const int sw = lane & 7;
+  float* myR = ring + lane;
+  bool prev_root_chunk = false;
+  unsigned int q = 0;
+  for (;; ++q) {
+    const int b = q & 1;
+    const bool live = tC >= 0;                                              // false: the drain chunk after the last tile
+    if (live) mbar_wait(bar_s + 8 * b, (q >> 1) & 1);
+    float4* bP = reinterpret_cast<float4*>(tiles + b * kStageBytes) + lane * 8;
+    float4* bV = bP + kPlaneTile / 16;
+    const bool root_chunk = !live || cC == 0;
+    if (root_chunk) {
+#pragma unroll 1
+      for (int j = 0; j < kK; ++j)
+        stream_step<PM, ORIGIN, true>(a, nz, s, j, prev_root_chunk && j == 0, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < kK; ++j)
+        stream_step<PM, ORIGIN, false>(a, nz, s, j, prev_root_chunk && j == 0, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    }
+    prev_root_chunk = root_chunk;
+    fence_async_smem();                                                     // generic-proxy writes -> visible to the TMA store
+    __syncwarp();
+    if (lane == 0) {
+      if (tS >= 0) issue_store(tS, cS, b);
+      if (tL >= 0 || !live) tma_wait_read0();                               // buffer b is free again
+      if (tL >= 0) issue_load(tL, cL, b);
+    }
+    if (!live) break;
+    tS = tC; cS = cC;
+    tC = tN; cC = cN;
+    tN = tL; cN = cL;
+    next_pos(tL, cL);
+    if (tC < 0 && lane == 0) tma_wait_read0();                              // the drain chunk reuses buffer b^1
+    __syncwarp();
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// A plane as a 2-D tensor of fp32: row = strand (stride nverts * 16 B), 4 * nverts floats per row; box = 32 floats x 32 rows.
+bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nverts) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = { (cuuint64_t)nverts * 4, (cuuint64_t)nstrands };
+  const cuuint64_t strides[1] = { (cuuint64_t)nverts * 16 };
+  const cuuint32_t box[2] = { 32, 32 };
+  const cuuint32_t estr[2] = { 1, 1 };
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct DeviceInfo { int sms = 0; bool ready[4] = { false, false, false, false }; int blocks_per_sm[4] = { 0, 0, 0, 0 }; };
+
+template <class PM, bool ORIGIN>
+cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int* tile_counter, int variant) {
+  static DeviceInfo info[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  auto kernel = hair_step_stream_kernel<PM, ORIGIN>;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    DeviceInfo& di = info[dev];
+    if (!di.ready[variant]) {
+      if ((e = cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.blocks_per_sm[variant], kernel, kThreads, kSmemBytes)) != cudaSuccess) return e;
+      if (di.blocks_per_sm[variant] < 1) return cudaErrorLaunchOutOfResources;
+      di.ready[variant] = true;
+    }
+  }
+  CUtensorMap mapP, mapV;
+  if (!make_plane_map(&mapP, a.pos, a.nstrands, a.nverts) || !make_plane_map(&mapV, a.vel, a.nstrands, a.nverts))
+    return cudaErrorInvalidValue;
+  const long long ntiles = (a.nstrands + 31) / 32;
+  long long blocks = (ntiles + kWarps - 1) / kWarps;
+  const long long resident = (long long)info[dev].sms * info[dev].blocks_per_sm[variant];
+  if (blocks > resident) blocks = resident;
+  if ((e = cudaMemsetAsync(tile_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+  kernel<<<(unsigned)blocks, kThreads, kSmemBytes, stream>>>(a, mapP, mapV, tile_counter, 0x8000000080000000ull);
+  return cudaGetLastError();
+}
+
+// Exhaustive check of the branch-free inverse square roots against the IEEE builtins: every binary32 in
+// [2^-64, 2^64), scalar (MathExact) and packed (PackedExact, both halves).
+__global__ void selftest_inversesqrt_kernel(unsigned long long* bad, const u64 nz) {
+  const unsigned int lo_bits = 0x1f800000u, hi_bits = 0x5f800000u;         // 2^-64, 2^64
+  unsigned long long nb = 0;
+  for (unsigned long long b = lo_bits + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < hi_bits;
+       b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((unsigned int)b);
+    const float want = __frcp_rn(__fsqrt_rn(x));
+    const float got_s = MathExact::inversesqrt_in_range(x);
+    const float x2 = __uint_as_float((unsigned int)(hi_bits - 1 - (b - lo_bits)));   // a different value in the other half
+    const u64 got_p = PackedExact::neg_inversesqrt_in_range(pk(x, x2), nz);
+    const float want2 = __frcp_rn(__fsqrt_rn(x2));
+    nb += (__float_as_uint(got_s) != __float_as_uint(want)) + (__float_as_uint(-lo(got_p)) != __float_as_uint(want)) +
+          (__float_as_uint(-hi(got_p)) != __float_as_uint(want2));
+  }
+  if (nb) atomicAdd(bad, nb);
+}
+
+}  // namespace
+
+cudaError_t selftest_inversesqrt(unsigned long long* mismatches) {
+  unsigned long long* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof *d);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(d, 0, sizeof *d);
+  if (e == cudaSuccess) { selftest_inversesqrt_kernel<<<148 * 8, 256>>>(d, 0x8000000080000000ull); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, sizeof *d, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e;
+}
+
+bool stream_kernel_eligible(const StepArgs& a) {
+  static const bool disabled = [] { const char* e = getenv("BH_NO_STREAM_KERNEL"); return e && e[0] == '1'; }();
+  return !disabled && a.iterations == kK && a.ncaps == 0 && a.nverts >= kK && a.nverts % kK == 0 &&
+         a.nstrands <= 0x7fffffffLL && a.r2 <= 1.8446744073709551616e19f && encode_tiled() != nullptr;
+}
+
+cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
+  // x - (+0.0f) == x bit for bit, for every x (a -0.0f centre component would turn a -0.0f coordinate into +0.0f)
+  const bool origin = __builtin_bit_cast(uint32_t, a.cx) == 0u && __builtin_bit_cast(uint32_t, a.cy) == 0u && __builtin_bit_cast(uint32_t, a.cz) == 0u;
+  if (math == 0) return origin ? launch_stream_t<PackedExact, true>(a, stream, tile_counter, 0) : launch_stream_t<PackedExact, false>(a, stream, tile_counter, 1);
+  return origin ? launch_stream_t<PackedFast, true>(a, stream, tile_counter, 2) : launch_stream_t<PackedFast, false>(a, stream, tile_counter, 3);
+}
+
+}  // namespace bh

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
     "bh_sphere_scalp_triangles", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
-    "bh_host_free", "bh_launch_count", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
+    "bh_host_free", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
 )
 
@@ -95,6 +95,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_launch_count": ([vp], i64),
+        "bh_step_kernel_kind": ([vp], C.c_int),
+        "bh_selftest_math": ([C.c_int, C.POINTER(C.c_uint64)], C.c_int),
         "bh_set_skin": ([vp, vp, vp, vp], C.c_int),
         "bh_skin_roots": ([vp, vp, C.c_int], C.c_int),
         "bh_register_gl_buffer": ([vp, C.c_uint], C.c_int),
@@ -136,6 +138,13 @@ def random_values(seed: int, first: int, count: int) -> np.ndarray:
     out = np.empty(count, np.float32)
     _check(load_library().bh_random_values(seed, first, count, _ptr(out)))
     return out
+
+
+def selftest_math(device: int = 0) -> int:
+    """Mismatch count of the exhaustive 1/sqrt check (must be 0)."""
+    bad = C.c_uint64()
+    _check(load_library().bh_selftest_math(device, C.byref(bad)))
+    return int(bad.value)
 
 
 def sphere_scalp_triangles(rows: int, cols: int) -> np.ndarray:
@@ -289,6 +298,11 @@ class HairSim:
     @property
     def launch_count(self) -> int:
         return int(self._lib.bh_launch_count(self._h))
+
+    @property
+    def kernel_kind(self) -> int:
+        """0 streaming, 1 per-strand pipelined, 2 generic (bh_step_kernel_kind)."""
+        return int(self._lib.bh_step_kernel_kind(self._h))
 
     # -- extensions --------------------------------------------------------------------------
     def set_skin(self, rest_root_pos3, joints4, weights3):

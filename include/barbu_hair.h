@@ -117,6 +117,12 @@ int  bh_host_alloc(void** ptr, uint64_t nbytes);     /* cudaMallocHost */
 int  bh_host_free(void* ptr);
 /* Kernel launches issued by this sim so far (bench.py's gpu_launches claim). */
 int64_t bh_launch_count(const bh_sim* sim);
+/* Which step kernel the current shape/parameters select: 0 streaming (TMA tiles + packed fp32x2; nverts % 8 == 0,
+ * 8 iterations, no capsules), 1 per-strand pipelined (any nverts), 2 generic (any iteration count). */
+int  bh_step_kernel_kind(const bh_sim* sim);
+/* Exhaustive device check of the exact profile's branch-free 1/sqrt(x) (scalar and packed fp32x2 forms) against
+ * the IEEE-754 builtins over every binary32 in [2^-64, 2^64). *mismatches must come back 0. */
+int  bh_selftest_math(int device, uint64_t* mismatches);
 
 /* ---- extension: dual-quaternion skinned roots (formula of shared/inc_skinning.glsl:22-31,54-82) */
 /* Stores rest roots + skin data once; bh_skin_roots rewrites vertex 0 of every strand in plane 0. */

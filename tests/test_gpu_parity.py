@@ -300,3 +300,58 @@ def test_hair_module_mirror():
     assert_bit_equal(gt2, gt, "tangent plane untouched by the simulation")
     hair.deinit()
     assert not hair.initialized()
+
+
+# ---- streaming kernel (TMA tiles, persistent warps, packed fp32x2) ---------------------------------
+
+def test_exact_inversesqrt_exhaustive():
+    """Branch-free 1/sqrt(x) of the exact profile == __frcp_rn(__fsqrt_rn(x)) for every float in [2^-64, 2^64)."""
+    assert bb.selftest_math(0) == 0
+
+
+@pytest.mark.parametrize("N", [8, 16, 24, 32, 64, 128])
+@pytest.mark.parametrize("S", [1, 31, 32, 33, 1000, 20000])
+def test_stream_kernel_bit_exact(S, N):
+    """Shapes that select the streaming kernel: ragged last tile, one chunk per strand (N=8), many tiles per warp."""
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.2, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(2):
+        po.step(rp, rv, S, N, par)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.2, sphere=SPHERE)
+        assert sim.kernel_kind == 0
+        sim.upload(pos, vel)
+        for _ in range(2):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+
+
+def test_stream_kernel_off_origin_sphere_bit_exact():
+    S, N = 3000, 32
+    sphere = (0.1, -0.05, 0.2, 0.9)
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.3, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(3):
+        po.step(rp, rv, S, N, par)
+    gp, gv = gpu_steps(pos, vel, S, N, 3, scale=1.3, sphere=sphere)
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+
+
+def test_stream_and_per_strand_kernels_agree(monkeypatch):
+    """Same state through bh_step (streaming kernel) and through a 9-iteration-free path: compare with the oracle at a
+    size where every resident warp owns several tiles (persistent scheduler, pipeline carried across tiles)."""
+    rows, cols, N = 256, 512, 16                      # 131,072 strands = 4,096 tiles > 148 SMs x 12 warps
+    S = rows * cols
+    _, _, _, _, pos, vel = sphere_state(rows, cols, N)
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(4):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    gp, gv = gpu_steps(pos, vel, S, N, 4, scale=1.45, sphere=SPHERE)
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
