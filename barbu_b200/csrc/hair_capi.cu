@@ -162,6 +162,11 @@ int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
   bh_default_params(&s->params);
   cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&s->tile_counters, sizeof(unsigned int) * 32 * (kHostPipeStreams + 1));
+  if (e == cudaSuccess) {
+    unsigned int words[32 * (kHostPipeStreams + 1)] = { 0 };
+    for (int i = 0; i <= kHostPipeStreams; ++i) bh::init_sched_words(words + 32 * i);
+    e = cudaMemcpy(s->tile_counters, words, sizeof words, cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
   for (int i = 0; i < kHostPipeStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
   if (e != cudaSuccess) { (void)cudaGetLastError(); bh_destroy(s); return fail(BH_ERR_CUDA, "bh_create: allocation", e); }

@@ -211,8 +211,8 @@ __device__ __forceinline__ void steady_step(const StepArgs& a, Pipe& s, float4* 
   // ---- phase B: push-outs, only when some lane of the warp touches the sphere ------------------
   V3 C[K - 1];
   if (__any_sync(0xffffffffu, mnc < a.r2)) {
-    // a hit has dpc < r2 <= 2^64 (launcher guarantees), so only the lower bound of the fast range can fail
-    inversesqrt_batch<M>(dpc, invc, !(mnc < 5.42101086242752217e-20f));
+    // a hit has dpc < r2 < inf (launcher guarantees), so only the lower bound of the fast range can fail
+    inversesqrt_batch<M>(dpc, invc, !(mnc < M::kFastLo));
 #pragma unroll
     for (int k = 0; k < K - 1; ++k) {
       const bool hit = dpc[k] < a.r2;

@@ -28,8 +28,11 @@ struct StepArgs {
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.
-// math: 0 exact, 1 fast. `tile_counter`: 4 bytes of device scratch owned by the caller and not shared with
-// any launch that may run concurrently (the streaming kernel's tile scheduler). Returns the CUDA error.
+// math: 0 exact, 1 fast. `tile_counter`: kSchedWords 32-bit words of device scratch owned by the caller, initialised
+// with init_sched_words() and not shared with any launch that may run concurrently (words 0-1: the streaming kernel's
+// tile scheduler, left zero again by every launch; words 2-3: the constant (-0.0f, -0.0f)). Returns the CUDA error.
+constexpr int kSchedWords = 4;
+inline void init_sched_words(unsigned int* host_words) { host_words[0] = host_words[1] = 0u; host_words[2] = host_words[3] = 0x80000000u; }
 cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 
 // Which kernel launch_step picks: 0 = streaming (hair_stream.cu), 1 = per-strand pipelined, 2 = generic.

@@ -101,7 +101,7 @@ struct PackedExact {
   static constexpr bool kRangeChecked = true;
   static __device__ __forceinline__ u64 mul(u64 a, u64 b, u64 nz) { return fma2(a, b, nz); }   // RN(a*b + -0) == RN(a*b), sign of zero included
   static __device__ __forceinline__ u64 dot(V3p a, V3p b, u64 nz) { return add2(add2(mul(a.x, b.x, nz), mul(a.y, b.y, nz)), mul(a.z, b.z, nz)); }
-  // -(1 / sqrt(x)) for both halves, x in [2^-64, 2^64): the sequence of MathExact::inversesqrt_in_range, with the
+  // -(1 / sqrt(x)) for both halves, finite x >= 2^-102: the sequence of MathExact::inversesqrt_in_range, with the
   // reciprocal seeded by rcp(-s) so that no packed negation is needed afterwards (RN is sign-symmetric).
   static __device__ __forceinline__ u64 neg_inversesqrt_in_range(u64 x, u64 nz) {
     const u64 y = pk(rsq_approx(lo(x)), rsq_approx(hi(x)));
@@ -160,23 +160,32 @@ __device__ __forceinline__ V3 root_transform(V3 p) {
 }
 
 // Pipeline registers. Pair a holds stages a (lo) and a + 4 (hi).
+//
+// X[k] is D(., k+1) as stage k left it in the previous step. The vertex now in stage k was in stage k-1 then, so its
+// input C(i, k) equals X[k-1] of the previous step unless the collider moved it. Collisions are rare per warp-step, so
+// the common step (SEP = false) reads its inputs straight from X shifted by one stage — nothing is copied from step to
+// step — and only a step that follows a push-out (SEP = true) reads the separately kept C values in P.
 struct Pipe {
-  V3p X[4];        // D(i-1, k+1): the already projected previous vertex of each stage
-  V3p P[4];        // C(i, k): input of each stage
+  V3p X[4];        // D of each stage, previous step; hi half of X[3] is D(i, 8) of the vertex waiting for d_{i+1}
+  V3p P[4];        // C(i, k): input of each stage; valid only after a step with a push-out
   u64 L[4];        // sf * rest_i of the vertex in each stage
-  V3 heldD, heldd; // D(i, 8) and d_i of the vertex waiting for d_{i+1}
+  V3 heldd;        // d_i of the vertex waiting for d_{i+1}
   V3 rootV;        // velocity written for the root that entered last
+  // collision of the vertex waiting for d_{i+1} (its position is final, its velocity is reflected one step later);
+  // written by a push-out step, read by the SEP step that follows it
+  V3 heldC, heldN;
+  bool heldHit;
 };
 
 template <class PM> __device__ __noinline__ u64 neg_inversesqrt_slow(u64 x) { return PM::neg_inversesqrt_ieee(x); }
 
-// ninv[a] = -inversesqrt(x[a]); the (rare) IEEE-builtin path is taken by the whole warp or not at all.
+// ninv[a] = -inversesqrt(x[a]). The branch-free sequence is issued unconditionally; when some lane of the warp has an
+// operand outside its range (`ok` false: rare), the whole warp recomputes with the IEEE builtins.
 template <class PM>
 __device__ __forceinline__ void neg_inversesqrt_batch(const u64 (&x)[4], u64 (&ninv)[4], bool ok, u64 nz) {
-  if (!PM::kRangeChecked || __all_sync(0xffffffffu, ok)) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) ninv[a] = PM::neg_inversesqrt_in_range(x[a], nz);
-  } else {
+  for (int a = 0; a < 4; ++a) ninv[a] = PM::neg_inversesqrt_in_range(x[a], nz);
+  if (PM::kRangeChecked && !__all_sync(0xffffffffu, ok)) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) ninv[a] = neg_inversesqrt_slow<PM>(x[a]);
   }
@@ -189,20 +198,23 @@ __device__ __forceinline__ float max8(const u64 (&v)[4]) {
   return fmaxf(fmaxf(fmaxf(lo(v[0]), hi(v[0])), fmaxf(lo(v[1]), hi(v[1]))), fmaxf(fmaxf(lo(v[2]), hi(v[2])), fmaxf(lo(v[3]), hi(v[3]))));
 }
 
-// One step of the stream pipeline: slot j of the current chunk.
+// One step of the stream pipeline: slot j of the current chunk. Returns whether any lane was pushed out of the
+// collider (warp-uniform), i.e. whether the next step must be the SEP variant.
 //   ROOT : this chunk starts a strand (vertex 0 is in slot 0), so at step j stage j holds a root, and step 7 finalises
 //          the tip of the previous strand.
+//   SEP  : the previous step had a push-out; inputs come from s.P.
 //   fin_root (runtime, warp-uniform): the vertex finalised by this step is a root.
-template <class PM, bool ORIGIN, bool ROOT>
-__device__ __forceinline__ void stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
+template <class PM, bool ORIGIN, bool ROOT, bool SEP>
+__device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
                                             float4* slotP, float4* slotV, float* slotR) {
   typedef typename PM::S M;
   const float rest_out = *slotR;
   const V3 rootV_out = s.rootV;
+  V3 x;
+  float lx;
   {
     const float4 Pin = *slotP, Vin = *slotV;
     *slotR = Pin.w;
-    V3 x;
     if (ROOT && j == 0) {
       x = root_transform<M>(V3{ Pin.x, Pin.y, Pin.z });
       s.rootV = vsub<M>(x, V3{ Pin.x, Pin.y, Pin.z });                      // p.velocity = p.position - lastPosition (cs:192)
@@ -212,105 +224,130 @@ __device__ __forceinline__ void stream_step(const StepArgs& a, const u64 nz, Pip
       x = { __fmaf_rn(a.dt2, a.fx, __fmaf_rn(a.dt, V.x, Pin.x)), __fmaf_rn(a.dt2, a.fy, __fmaf_rn(a.dt, V.y, Pin.y)),
             __fmaf_rn(a.dt2, a.fz, __fmaf_rn(a.dt, V.z, Pin.z)) };         // cs:181-182
     }
-    s.P[0] = pk3(x, hi3(s.P[0]));
-    s.L[0] = pk(M::mul(a.sf, Pin.w), hi(s.L[0]));
+    lx = M::mul(a.sf, Pin.w);
   }
+  // ---- the vertex finalised by this step (t-8): position known since the previous step ------------
+  const V3 fin = hi3(s.X[3]);                                               // D(i, 8)
+  V3 fp = fin;
+  if (SEP) { fp.x = s.heldHit ? s.heldC.x : fin.x; fp.y = s.heldHit ? s.heldC.y : fin.y; fp.z = s.heldHit ? s.heldC.z : fin.z; }
+  float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out);
+
+  // inputs of the eight stages: stage 0 takes the new vertex, stage k > 0 what stage k-1 produced in the previous step
+  V3p in[4];
+  in[0] = pk3(x, SEP ? hi3(s.P[0]) : lo3(s.X[3]));
+#pragma unroll
+  for (int q = 1; q < 4; ++q) in[q] = SEP ? s.P[q] : s.X[q - 1];
+  // sf * rest moves along with its vertex
+  const float l3 = lo(s.L[3]);
+#pragma unroll
+  for (int q = 3; q >= 1; --q) s.L[q] = s.L[q - 1];
+  s.L[0] = pk(lx, l3);
+
   // ---- phase A: the eight projections, as four packed chains ---------------------------------------
   V3p vd[4], D[4];
   u64 dp[4], ninv[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    vd[q] = sub3(s.P[q], s.X[q]);
+    vd[q] = sub3(in[q], s.X[q]);
     dp[q] = PM::dot(vd[q], vd[q], nz);
   }
   bool ok = true;
-  if (PM::kRangeChecked) ok = M::in_fast_range(min8(dp)) && M::in_fast_range(max8(dp));   // NaN stays NaN on both paths
+  if (PM::kRangeChecked) {                                                  // all eight operands inside the branch-free range?
+    unsigned key = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) key = max(key, max(M::range_key(lo(dp[q])), M::range_key(hi(dp[q]))));
+    ok = key < M::kRangeKeyEnd;
+  }
   neg_inversesqrt_batch<PM>(dp, ninv, ok, nz);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) D[q] = PM::project(s.X[q], vd[q], ninv[q], s.L[q], nz);
-  if (ROOT) {                                                               // the root passes through: D(0, k) = X[0]
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (j == q) D[q] = pk3(lo3(s.P[q]), hi3(D[q]));
-      if (j == q + 4) D[q] = pk3(lo3(D[q]), hi3(s.P[q]));
+  for (int q = 3; q >= 0; --q) {
+    D[q] = PM::project(s.X[q], vd[q], ninv[q], s.L[q], nz);
+    if (ROOT) {                                                             // the root passes through: D(0, k) = X[0]
+      if (j == q) D[q] = pk3(lo3(in[q]), hi3(D[q]));
+      if (j == q + 4) D[q] = pk3(lo3(D[q]), hi3(in[q]));
     }
+    if (q == 3) {
+      const V3 dF = vsub<M>(hi3(D[3]), hi3(in[3]));                         // s_particles[i].velocity = p1_bis - p1 (cs:116)
+      V3 fw = M::scale(dF, a.damp);                                         // cs:119-121
+      if (ROOT && j == 7) fw = s.heldd;                                     // the tip keeps its own d
+      s.heldd = dF;
+      if (SEP && s.heldHit) fw = M::reflect(fw, s.heldN);                   // cs:137, with the normal found one step ago
+      float4 oV = make_float4(fw.x, fw.y, fw.z, 0.f);
+      if (fin_root) oV = make_float4(rootV_out.x, rootV_out.y, rootV_out.z, 0.f);   // a root is neither moved nor reflected
+      *slotP = oP;
+      *slotV = oV;
+    }
+    s.X[q] = D[q];
   }
-  const V3 D7 = hi3(D[3]);
-  const V3 dF = vsub<M>(D7, hi3(s.P[3]));                                   // s_particles[i].velocity = p1_bis - p1 (cs:116)
-  V3 fp = s.heldD;                                                          // the vertex being finalised: t-8
-  V3 fw = M::scale(dF, a.damp);                                             // cs:119-121
-  if (ROOT && j == 7) fw = s.heldd;                                         // the tip keeps its own d
 
-  // ---- phase T: collision tests; the hi half of pair 3 is the finalised vertex (stage 7 is tested next step) ----
+  // ---- phase T: collision tests of the eight new positions -----------------------------------------
   const V3p c2 = { pk(a.cx, a.cx), pk(a.cy, a.cy), pk(a.cz, a.cz) };
-  V3p T[4], pt[4];
+  V3p pt[4];
   u64 dpc[4];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) T[q] = D[q];
-  T[3] = pk3(lo3(D[3]), fp);
-#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    pt[q] = ORIGIN ? T[q] : sub3(T[q], c2);
+    pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
     dpc[q] = PM::dot(pt[q], pt[q], nz);
   }
   if (ROOT) {                                                               // roots do not collide (cs:149-151: index > 0)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (j == q) dpc[q] = pk(__int_as_float(0x7f800000), hi(dpc[q]));
-      if (q < 3 && j == q + 4) dpc[q] = pk(lo(dpc[q]), __int_as_float(0x7f800000));
+      if (j == q + 4) dpc[q] = pk(lo(dpc[q]), __int_as_float(0x7f800000));
     }
   }
   const float mnc = min8(dpc);
 
   // ---- phase B: push-outs, only when some lane of the warp touches the sphere --------------------
-  V3p C[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) C[q] = T[q];
-  if (__any_sync(0xffffffffu, mnc < a.r2)) {
-    // a hit has dpc < r2 <= 2^64 (launcher guarantees), so only the lower bound of the fast range can fail
+  const bool any_hit = __any_sync(0xffffffffu, mnc < a.r2);
+  if (any_hit) {
+    // a hit has dpc < r2 < inf (launcher guarantees), so only the lower bound of the branch-free range can fail
     u64 ninvc[4];
-    neg_inversesqrt_batch<PM>(dpc, ninvc, !(mnc < 5.42101086242752217e-20f), nz);
+    neg_inversesqrt_batch<PM>(dpc, ninvc, !(mnc < M::kFastLo), nz);
     const u64 r2p = pk(a.r, a.r);
+    V3p C[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const V3p Q = PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
       const bool hl = lo(dpc[q]) < a.r2, hh = hi(dpc[q]) < a.r2;
-      C[q].x = pk(hl ? lo(Q.x) : lo(T[q].x), hh ? hi(Q.x) : hi(T[q].x));
-      C[q].y = pk(hl ? lo(Q.y) : lo(T[q].y), hh ? hi(Q.y) : hi(T[q].y));
-      C[q].z = pk(hl ? lo(Q.z) : lo(T[q].z), hh ? hi(Q.z) : hi(T[q].z));
+      C[q].x = pk(hl ? lo(Q.x) : lo(D[q].x), hh ? hi(Q.x) : hi(D[q].x));
+      C[q].y = pk(hl ? lo(Q.y) : lo(D[q].y), hh ? hi(Q.y) : hi(D[q].y));
+      C[q].z = pk(hl ? lo(Q.z) : lo(D[q].z), hh ? hi(Q.z) : hi(D[q].z));
     }
-    if (hi(dpc[3]) < a.r2) {                                                // the finalised vertex: vel = reflect(vel, n)
-      const float inv = PM::inv_of(hi(ninvc[3]));
-      const V3 n = M::scale(hi3(pt[3]), inv);
-      fw = M::reflect(fw, n);
-    }
+    // stage 7 is done: keep its final position and the collision normal for the step that writes it out
+    s.heldHit = hi(dpc[3]) < a.r2;
+    s.heldC = hi3(C[3]);
+    s.heldN = M::scale(hi3(pt[3]), PM::inv_of(hi(ninvc[3])));
+    // the moved vertices enter the next step through P: stage k+1 takes C of stage k
+#pragma unroll
+    for (int q = 3; q >= 1; --q) s.P[q] = C[q - 1];
+    s.P[0] = pk3(V3{ 0.f, 0.f, 0.f }, lo3(C[3]));
   }
-  fp = hi3(C[3]);
+  return any_hit;
+}
 
-  // ---- commit ------------------------------------------------------------------------------------
-  float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out), oV = make_float4(fw.x, fw.y, fw.z, 0.f);
-  if (fin_root) {                                                           // root: position as transformed, no collision
-    oP = make_float4(s.heldD.x, s.heldD.y, s.heldD.z, rest_out);
-    oV = make_float4(rootV_out.x, rootV_out.y, rootV_out.z, 0.f);
+// The eight steps of one chunk; `sep` carries the push-out state from step to step.
+template <class PM, bool ORIGIN, bool ROOT>
+__device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pipe& s, bool& sep, const bool prev_root_chunk,
+                                             float4* bP, float4* bV, float* myR, const int sw) {
+#pragma unroll 1
+  for (int j = 0; j < kK; ++j) {
+    const bool fin_root = prev_root_chunk && j == 0;
+    if (sep) sep = stream_step<PM, ORIGIN, ROOT, true>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    else sep = stream_step<PM, ORIGIN, ROOT, false>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
   }
-  *slotP = oP;
-  *slotV = oV;
-  s.heldD = D7; s.heldd = dF;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) s.X[q] = D[q];
-  // vertex moves to the next stage: pair q -> pair q+1; stage 3 -> stage 4 (lo of pair 3 -> hi of pair 0)
-  const V3 c3 = lo3(C[3]);
-  const float l3 = lo(s.L[3]);
-#pragma unroll
-  for (int q = 3; q >= 1; --q) { s.P[q] = C[q - 1]; s.L[q] = s.L[q - 1]; }
-  s.P[0] = pk3(V3{ 0.f, 0.f, 0.f }, c3);
-  s.L[0] = pk(0.f, l3);
 }
 
 template <class PM, bool ORIGIN>
-__global__ void __launch_bounds__(kThreads, 3)
+#ifndef BH_STREAM_MINB
+#define BH_STREAM_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, BH_STREAM_MINB)
 hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap mapP,
-                        const __grid_constant__ CUtensorMap mapV, unsigned int* __restrict__ tile_counter, const u64 nz) {
+                        const __grid_constant__ CUtensorMap mapV, unsigned int* tile_counter) {
+  // (-0.0f, -0.0f), read from device memory: a value ptxas can neither fold into the packed products (it would then
+  // contract them with the following add) nor re-load from the constant bank in the middle of the step
+  const u64 nz = *reinterpret_cast<const u64*>(tile_counter + 2);
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -351,8 +388,15 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   };
 
   // chunk positions: S = being stored (q-1), C = being computed (q), N = loaded (q+1), L = next to load (q+2)
+  // The last warp of the grid to leave puts both words back to zero: no memset between launches.
+  auto leave = [&]() {
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) { tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence(); }
+    }
+  };
   int tC = grab(), cC = 0;
-  if (tC < 0) return;
+  if (tC < 0) { leave(); return; }
   auto next_pos = [&](int& t, int& c) {
     if (t < 0) return;
     if (++c == chunks) { c = 0; t = grab(); }
@@ -373,14 +417,14 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       const u64 x = pk(1.0e3f + 10.f * q, 1.0e3f + 10.f * (q + 4)), p = pk(1.0e3f + 10.f * q + 10.f, 1.0e3f + 10.f * (q + 4) + 10.f);
       s.X[q] = { x, x, x }; s.P[q] = { p, p, p }; s.L[q] = 0ull;
     }
-    s.heldD = { 1.0e3f, 1.0e3f, 1.0e3f };
-    s.heldd = s.rootV = { 0.f, 0.f, 0.f };
+    s.heldd = s.rootV = s.heldC = s.heldN = { 0.f, 0.f, 0.f };
+    s.heldHit = false;
   }
   for (int j = 0; j < kK; ++j) ring[j * 32 + lane] = 0.f;
 
   const int sw = lane & 7;
   float* myR = ring + lane;
-  bool prev_root_chunk = false;
+  bool prev_root_chunk = false, sep = false;
   unsigned int q = 0;
   for (;; ++q) {
     const int b = q & 1;
@@ -389,15 +433,8 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     float4* bP = reinterpret_cast<float4*>(tiles + b * kStageBytes) + lane * 8;
     float4* bV = bP + kPlaneTile / 16;
     const bool root_chunk = !live || cC == 0;
-    if (root_chunk) {
-#pragma unroll 1
-      for (int j = 0; j < kK; ++j)
-        stream_step<PM, ORIGIN, true>(a, nz, s, j, prev_root_chunk && j == 0, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < kK; ++j)
-        stream_step<PM, ORIGIN, false>(a, nz, s, j, prev_root_chunk && j == 0, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
-    }
+    if (root_chunk) stream_chunk<PM, ORIGIN, true>(a, nz, s, sep, prev_root_chunk, bP, bV, myR, sw);
+    else stream_chunk<PM, ORIGIN, false>(a, nz, s, sep, prev_root_chunk, bP, bV, myR, sw);
     prev_root_chunk = root_chunk;
     fence_async_smem();                                                     // generic-proxy writes -> visible to the TMA store
     __syncwarp();
@@ -414,6 +451,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     if (tC < 0 && lane == 0) tma_wait_read0();                              // the drain chunk reuses buffer b^1
     __syncwarp();
   }
+  leave();
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -470,17 +508,19 @@ cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int
     return cudaErrorInvalidValue;
   const long long ntiles = (a.nstrands + 31) / 32;
   long long blocks = (ntiles + kWarps - 1) / kWarps;
-  const long long resident = (long long)info[dev].sms * info[dev].blocks_per_sm[variant];
+  static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
+  int per_sm = info[dev].blocks_per_sm[variant];
+  if (occ_cap > 0 && occ_cap < per_sm) per_sm = occ_cap;
+  const long long resident = (long long)info[dev].sms * per_sm;
   if (blocks > resident) blocks = resident;
-  if ((e = cudaMemsetAsync(tile_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-  kernel<<<(unsigned)blocks, kThreads, kSmemBytes, stream>>>(a, mapP, mapV, tile_counter, 0x8000000080000000ull);
+  kernel<<<(unsigned)blocks, kThreads, kSmemBytes, stream>>>(a, mapP, mapV, tile_counter);
   return cudaGetLastError();
 }
 
-// Exhaustive check of the branch-free inverse square roots against the IEEE builtins: every binary32 in
-// [2^-64, 2^64), scalar (MathExact) and packed (PackedExact, both halves).
+// Exhaustive check of the branch-free inverse square roots against the IEEE builtins: every finite binary32
+// >= 2^-102, scalar (MathExact) and packed (PackedExact, both halves).
 __global__ void selftest_inversesqrt_kernel(unsigned long long* bad, const u64 nz) {
-  const unsigned int lo_bits = 0x1f800000u, hi_bits = 0x5f800000u;         // 2^-64, 2^64
+  const unsigned int lo_bits = 0x0C800000u, hi_bits = 0x7F800000u;         // 2^-102, +inf
   unsigned long long nb = 0;
   for (unsigned long long b = lo_bits + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < hi_bits;
        b += (unsigned long long)gridDim.x * blockDim.x) {

@@ -121,7 +121,7 @@ int64_t bh_launch_count(const bh_sim* sim);
  * 8 iterations, no capsules), 1 per-strand pipelined (any nverts), 2 generic (any iteration count). */
 int  bh_step_kernel_kind(const bh_sim* sim);
 /* Exhaustive device check of the exact profile's branch-free 1/sqrt(x) (scalar and packed fp32x2 forms) against
- * the IEEE-754 builtins over every binary32 in [2^-64, 2^64). *mismatches must come back 0. */
+ * the IEEE-754 builtins over every finite binary32 >= 2^-102. *mismatches must come back 0. */
 int  bh_selftest_math(int device, uint64_t* mismatches);
 
 /* ---- extension: dual-quaternion skinned roots (formula of shared/inc_skinning.glsl:22-31,54-82) */
