@@ -50,5 +50,24 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+ADAPTOR_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "hair_adaptor_main.cc")
+ADAPTOR_BIN = os.path.join(LIB_DIR, "hair_adaptor_main")
+
+
+def build_cpp_adaptor_driver(force=False):
+    """g++ -std=c++17 build of the C++ `Hair` adaptor driver (tests/cpp) against libbarbu_hair.so — host compiler only:
+    the adaptor header needs neither CUDA nor GL headers."""
+    hdrs = [os.path.join(os.path.dirname(HERE), "include", h) for h in ("barbu_hair.h", "barbu_hair.hpp")]
+    if not force and os.path.exists(ADAPTOR_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(ADAPTOR_BIN)
+                                                          for d in hdrs + [ADAPTOR_SRC, LIB_PATH]):
+        return ADAPTOR_BIN
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", ADAPTOR_BIN, ADAPTOR_SRC,
+           "-L" + LIB_DIR, "-lbarbu_hair", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return ADAPTOR_BIN
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
