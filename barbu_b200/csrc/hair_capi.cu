@@ -40,7 +40,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e__ != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, #expr, e__); } \
   } while (0)
 
-constexpr int kHostPipeStreams = 3;
+constexpr int kHostPipeStreams = 4;
 
 }  // namespace
 
@@ -53,7 +53,7 @@ struct bh_sim {
   float4* planes[BH_NUM_PLANES] = { nullptr, nullptr, nullptr };
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaStream_t pipe[kHostPipeStreams] = { nullptr, nullptr, nullptr };
+  cudaStream_t pipe[kHostPipeStreams] = { nullptr, nullptr, nullptr, nullptr };
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
   int64_t launches = 0;
@@ -381,7 +381,7 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
   // downloaded while its neighbours are still in flight: H2D, kernels and D2H of different slices
   // overlap on kHostPipeStreams streams (PCIe is full duplex).
   const int64_t S = s->nstrands;
-  int64_t slice = (S + 15) / 16;
+  int64_t slice = (S + 31) / 32;
   const int64_t min_slice = 4096;
   if (slice < min_slice) slice = min_slice;
   slice = (slice + 127) / 128 * 128;

@@ -175,7 +175,6 @@ def run_gpu(args, rank, world, local_rank):
 
     sim = bb.HairSim(S, NVERTS, device=local_rank)
     sim.configure(scale=SCALE, sphere=SPHERE, math=math)
-    sim.init_sphere_scalp(ROWS, cols_total, first, bb.random_values(SEED, first, S))
     stream = torch.cuda.Stream()                  # a real (non-default) stream owned by torch ...
     torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)            # ... that our kernels are launched on, so torch events bracket them
@@ -185,34 +184,54 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_region(math_id, sampler):
+        """W untimed steps (+ pre-roll so clocks settle), then exactly K steps between two CUDA events on the launching
+        stream, barrier + synchronize on both sides, max over ranks. Returns (ms_total, launches)."""
+        sim.configure(math=math_id)
+        sim.init_sphere_scalp(ROWS, cols_total, first, rv)        # every profile starts from the same cold state
+        t_w = time.perf_counter()
+        done = 0
+        while done < args.warmup or time.perf_counter() - t_w < args.preroll:
+            sim.step(DT, SUBSTEPS)
+            done += 1
+            if done % 16 == 0:
+                torch.cuda.synchronize()
+        barrier()
+        if sampler is not None:
+            sampler.mark_begin()
+        l0 = sim.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            sim.step(DT, SUBSTEPS)
+        ev1.record(stream)
+        barrier()
+        if sampler is not None:
+            sampler.mark_end()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), sim.launch_count - l0
+
     # ---- device-resident timing: value + roofline ---------------------------------------------------
+    rv = bb.random_values(SEED, first, S)
+    kernel_kind = sim.kernel_kind
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # warm-up: W untimed steps, continued for >= 0.4 s so clocks settle and the sampler has data before the timed region
-    t_w = time.perf_counter()
-    done = 0
-    while done < args.warmup or time.perf_counter() - t_w < args.preroll:
-        sim.step(DT, SUBSTEPS)
-        done += 1
-        if done % 16 == 0:
-            torch.cuda.synchronize()
-    barrier()
-    sampler.mark_begin()
-    l0 = sim.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        sim.step(DT, SUBSTEPS)
-    ev1.record(stream)
-    barrier()
-    sampler.mark_end()
-    launches = sim.launch_count - l0
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total, launches = timed_region(math, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
+    # the other arithmetic profile, same workload and timing rules (reported beside the headline, never instead of it)
+    other = None
+    if not args.no_other_profile:
+        other_math = bb.BH_MATH_EXACT if math == bb.BH_MATH_FAST else bb.BH_MATH_FAST
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms2, launches2 = timed_region(other_math, sampler2 if rank == 0 else None)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        other = (ms2, launches2, clocks2)
+        sim.configure(math=math)
 
     # ---- end to end through the C ABI with HOST buffers (bh_step_host): H2D + 4 substeps + D2H per step ---
     e2e_value, e2e_steps = None, 0
@@ -235,6 +254,30 @@ def run_gpu(args, rank, world, local_rank):
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e_value = world * V * SUBSTEPS * e2e_steps / float(t_e2e.item())
         hp.free(); hv.free()
+
+    # ---- optional exchange step (N > 1): all-gather of the position plane to every rank, NCCL over NVLink ----------
+    gather = None
+    if dist is not None and args.allgather:
+        from barbu_b200 import shard
+        local = shard.plane_tensor(sim, 0)
+        counts = [V] * world
+        sim.synchronize()
+        for _ in range(2):
+            full = shard.allgather_plane(local, counts)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        reps = 5
+        for _ in range(reps):
+            full = shard.allgather_plane(local, counts)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        recv = 16 * V * (world - 1)
+        gather = {"ms": float(gms.item()), "bytes_received_per_gpu": recv, "gbs_per_gpu": recv / (float(gms.item()) * 1e-3) / 1e9,
+                  "what": "ncclAllGather of the float4 position plane (optional, off the per-step path)"}
+        del full
     sim.close()
 
     if rank == 0:
@@ -245,6 +288,7 @@ def run_gpu(args, rank, world, local_rank):
         threads = host_threads()
         sample = 1 << 19
         cpu_value, _ = cpu_reference_time(sample, 1, 0, threads) if world == 1 and not args.no_cpu_baseline else (None, None)
+        kernel_names = {0: "hair_step_stream_kernel", 1: "hair_step_pipelined_kernel", 2: "hair_step_generic_kernel"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -253,7 +297,7 @@ def run_gpu(args, rank, world, local_rank):
                        "l2": "state 1 GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "hair_step_pipelined_kernel", "peak_source": peak_src,
+                         "traffic": None, "kernel": kernel_names.get(kernel_kind, "?"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V, "ms_per_launch": per_launch_s * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * V, "d2h_bytes_per_step": 32 * V,
                     "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)"},
@@ -264,10 +308,25 @@ def run_gpu(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} of {S} strands x {NVERTS} vertices x {SUBSTEPS} substeps, 1 step, "
                                               f"{threads} OpenMP threads; CPU restatement of the reference GLSL, not llvmpipe"}
+        traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.exists(traffic_file):
             with open(traffic_file) as f:
-                line["roofline"]["traffic"] = json.load(f).get(args.math)
+                traffic = json.load(f)
+        line["roofline"]["traffic"] = traffic.get(args.math)
+        if other is not None:
+            ms2, launches2, clocks2 = other
+            name2 = "exact" if args.math == "fast" else "fast"
+            per2 = ms2 * 1e-3 / launches2
+            ach2 = BYTES_PER_VERTEX_PER_LAUNCH * V / per2 / 1e9
+            line["other_profile"] = {"math": name2, "value": world * V * SUBSTEPS * args.steps / (ms2 * 1e-3), "unit": UNIT,
+                                     "ms_per_step": ms2 / args.steps, "gpu_launches": launches2, "clocks": clocks2,
+                                     "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                                                  "traffic": traffic.get(name2), "ms_per_launch": per2 * 1e3},
+                                     "note": "same workload, steps and timing rules; exact = bit-identical to the CPU oracle, "
+                                             "fast = FMA-contracted + MUFU.RSQ arithmetic (<= 1e-5 relative per vertex after one step)"}
+        if gather is not None:
+            line["allgather"] = gather
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -282,6 +341,8 @@ def main():
     ap.add_argument("--math", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-other-profile", action="store_true", help="time only the --math profile")
+    ap.add_argument("--allgather", action="store_true", help="N > 1: also time the optional NCCL all-gather of the position plane")
     ap.add_argument("--preroll", type=float, default=0.4, help="minimum seconds of untimed warm-up (0 for profiler runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_${TAG}.log
 for v in ${VARIANTS:-4:exact 4:fast 3:exact 3:fast}; do
   occ=${v%%:*}; m=${v##*:}
-  BH_SCHED_OCC=$occ timeout 600 python bench.py --steps 50 --warmup 3 --math $m --no-cpu-baseline --no-e2e > gpurun_out/bench_${m}_occ${occ}_${TAG}.json 2>gpurun_out/bench_${m}_occ${occ}_${TAG}.err
+  BH_SCHED_OCC=$occ timeout 600 python bench.py --steps 50 --warmup 3 --math $m --no-cpu-baseline --no-e2e --no-other-profile > gpurun_out/bench_${m}_occ${occ}_${TAG}.json 2>gpurun_out/bench_${m}_occ${occ}_${TAG}.err
   python - <<PY
 import json
 try:

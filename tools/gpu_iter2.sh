@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 if [ -n "$2" ]; then K=(-k "$2"); else K=(); fi
 timeout 1200 python -m pytest tests -m gpu -x -q "${K[@]}" > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_${TAG}.log
 for m in exact fast; do
-  timeout 600 python bench.py --steps ${STEPS:-50} --warmup 3 --math $m --no-cpu-baseline --no-e2e > gpurun_out/bench_${m}_${TAG}.json 2>gpurun_out/bench_${m}_${TAG}.err
+  timeout 600 python bench.py --steps ${STEPS:-50} --warmup 3 --math $m --no-cpu-baseline --no-e2e --no-other-profile > gpurun_out/bench_${m}_${TAG}.json 2>gpurun_out/bench_${m}_${TAG}.err
   python - <<PY
 import json
 try:
@@ -17,7 +17,7 @@ except Exception as e:
 PY
 done
 if [ -n "$NCU" ]; then
-  PROF="python bench.py --steps 2 --warmup 3 --preroll 0 --no-cpu-baseline --no-e2e"
+  PROF="python bench.py --steps 2 --warmup 3 --preroll 0 --no-cpu-baseline --no-e2e --no-other-profile"
   for m in ${MATHS:-exact fast}; do
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:hair_step_ -s 6 -c 1 \
         -f -o gpurun_out/prof_${m}_${TAG} $PROF --math $m > gpurun_out/ncu_full_${m}_${TAG}.log 2>&1
