@@ -503,9 +503,28 @@ cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int
       di.ready[variant] = true;
     }
   }
+  // Tensor maps are pure functions of (plane address, shape): keep the last few so a frame of substeps on the same
+  // shard (or the slices of bh_step_host) does not re-encode them at every launch.
+  struct MapEntry { const void* pos; const void* vel; long long s; int n; CUtensorMap mapP, mapV; };
+  static MapEntry cache[64];
+  static int cache_next = 0;
   CUtensorMap mapP, mapV;
-  if (!make_plane_map(&mapP, a.pos, a.nstrands, a.nverts) || !make_plane_map(&mapV, a.vel, a.nstrands, a.nverts))
-    return cudaErrorInvalidValue;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    const MapEntry* hit = nullptr;
+    for (const MapEntry& m : cache)
+      if (m.pos == a.pos && m.vel == a.vel && m.s == a.nstrands && m.n == a.nverts) { hit = &m; break; }
+    if (!hit) {
+      MapEntry& m = cache[cache_next];
+      cache_next = (cache_next + 1) % 64;
+      m.pos = nullptr;
+      if (!make_plane_map(&m.mapP, a.pos, a.nstrands, a.nverts) || !make_plane_map(&m.mapV, a.vel, a.nstrands, a.nverts))
+        return cudaErrorInvalidValue;
+      m.pos = a.pos; m.vel = a.vel; m.s = a.nstrands; m.n = a.nverts;
+      hit = &m;
+    }
+    mapP = hit->mapP; mapV = hit->mapV;
+  }
   const long long ntiles = (a.nstrands + 31) / 32;
   long long blocks = (ntiles + kWarps - 1) / kWarps;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob

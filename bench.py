@@ -165,6 +165,8 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     S = ROWS * COLS_PER_GPU                       # strands of this rank
@@ -189,6 +191,10 @@ def run_gpu(args, rank, world, local_rank):
         stream, barrier + synchronize on both sides, max over ranks. Returns (ms_total, launches)."""
         sim.configure(math=math_id)
         sim.init_sphere_scalp(ROWS, cols_total, first, rv)        # every profile starts from the same cold state
+        for i in range(args.settle):
+            sim.step(DT, SUBSTEPS)
+            if i % 16 == 15:
+                torch.cuda.synchronize()
         t_w = time.perf_counter()
         done = 0
         while done < args.warmup or time.perf_counter() - t_w < args.preroll:
@@ -209,11 +215,16 @@ def run_gpu(args, rank, world, local_rank):
         if sampler is not None:
             sampler.mark_end()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        per_rank = [float(ms.item())]
         if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), sim.launch_count - l0
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank = [float(x.item()) for x in allms]
+        per_rank_ms.append(per_rank)
+        return max(per_rank), sim.launch_count - l0
 
     # ---- device-resident timing: value + roofline ---------------------------------------------------
+    per_rank_ms = []
     rv = bb.random_values(SEED, first, S)
     kernel_kind = sim.kernel_kind
     sampler = ClockSampler(local_rank)
@@ -294,6 +305,7 @@ def run_gpu(args, rank, world, local_rank):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(world), "math": args.math, "iterations": 8,
+                       "state": f"settled: {args.settle} untimed frames from the cold state, then {args.warmup}+ warm-up steps",
                        "l2": "state 1 GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -304,6 +316,8 @@ def run_gpu(args, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world > 1:
+            line["ms_per_step_by_rank"] = [t / args.steps for t in per_rank_ms[0]]
         if cpu_value is not None:
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} of {S} strands x {NVERTS} vertices x {SUBSTEPS} substeps, 1 step, "
@@ -338,12 +352,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--math", default="fast", choices=["exact", "fast"],
+                    help="arithmetic profile of the headline numbers (the other one is timed too and reported in other_profile): "
+                         "fast = FMA contraction + MUFU.RSQ, what a GPU GLSL compiler emits for the reference shader, inside "
+                         "north_star's tolerance (<= 1e-5 relative per vertex after one step); exact = bit-identical to the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-other-profile", action="store_true", help="time only the --math profile")
     ap.add_argument("--allgather", action="store_true", help="N > 1: also time the optional NCCL all-gather of the position plane")
     ap.add_argument("--preroll", type=float, default=0.4, help="minimum seconds of untimed warm-up (0 for profiler runs)")
+    ap.add_argument("--settle", type=int, default=100,
+                    help="untimed frames run before the W warm-up steps so that the timed region sees the SETTLED hair (strands "
+                         "draped over the collider, push-outs in ~40%% of warp-steps), not the cold straight state, which is "
+                         "cheaper for the exact profile (0 for profiler runs that want the cold state)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

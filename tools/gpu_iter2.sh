@@ -17,7 +17,7 @@ except Exception as e:
 PY
 done
 if [ -n "$NCU" ]; then
-  PROF="python bench.py --steps 2 --warmup 3 --preroll 0 --no-cpu-baseline --no-e2e --no-other-profile"
+  PROF="python bench.py --steps 2 --warmup 3 --preroll 0 --settle 0 --no-cpu-baseline --no-e2e --no-other-profile"
   for m in ${MATHS:-exact fast}; do
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:hair_step_ -s 6 -c 1 \
         -f -o gpurun_out/prof_${m}_${TAG} $PROF --math $m > gpurun_out/ncu_full_${m}_${TAG}.log 2>&1

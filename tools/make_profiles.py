@@ -35,7 +35,9 @@ if os.path.exists(lf):
             tot[k] += ns; cnt[k] += 1
     s = sum(tot.values())
     with open(os.path.join(P, f"{rnd}_ncu_launches_summary.txt"), "w") as f:
-        f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 3 --preroll 0 --no-cpu-baseline\n")
+        f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none -s 412 -c 1200: python bench.py --steps 2 --warmup 3 --preroll 0 --no-cpu-baseline\n")
+        f.write("(the 412 skipped launches are the bench's 100 settle frames + 3 warm-up steps; listed: timed region of the headline profile,\n"
+                " settle + timed region of the other profile, and the bh_step_host slices of the e2e leg)\n")
         f.write("(cold-cache, serialised launch times: compare SHARES, not absolutes)\n\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"{100 * v / s:6.2f}%  {cnt[k]:4d} launches  {v / cnt[k] / 1e3:10.1f} us avg  {k}\n")
@@ -58,7 +60,7 @@ for m in ("exact", "fast"):
     raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
     h, u, d = raw[0], raw[1], raw[2]
     get = lambda k: d[h.index(k)] if k in h else "n/a"
-    out = [f"ncu --set full --clock-control none --import-source on -k regex:hair_step_ -s 6 -c 1: python bench.py --steps 2 --warmup 3 --preroll 0 --math {m}",
+    out = [f"ncu --set full --clock-control none --import-source on -k regex:hair_step_ -s 412 -c 1: python bench.py --steps 2 --warmup 3 --preroll 0 --math {m}  (settled state: launch 413)",
            f"kernel: {get('Kernel Name')}", ""]
     for k in KEYS:
         out.append(f"  {k:72s} {get(k):>18s} {u[h.index(k)] if k in h else ''}")
