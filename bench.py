@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-other-profile", action="store_true", help="time only the --math profile")
     ap.add_argument("--allgather", action="store_true", help="N > 1: also time the optional NCCL all-gather of the position plane")
-    ap.add_argument("--preroll", type=float, default=0.4, help="minimum seconds of untimed warm-up (0 for profiler runs)")
+    ap.add_argument("--preroll", type=float, default=0.0, help="minimum seconds of untimed warm-up (0 for profiler runs)")
     ap.add_argument("--settle", type=int, default=100,
                     help="untimed frames run before the W warm-up steps so that the timed region sees the SETTLED hair (strands "
                          "draped over the collider, push-outs in ~40%% of warp-steps), not the cold straight state, which is "
