@@ -9,7 +9,13 @@
 #include "../../include/barbu_hair.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
 
 namespace {
 
@@ -112,5 +118,80 @@ int bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri) {
     }
   return BH_OK;
 }
+
+// ---- scalp input: Wavefront OBJ as the reference's mesh loader reads it -------------------------------------------------
+// ParseOBJ (src/memory/resources/mesh_data_manager.cc:69-223): one pass over '\n'-terminated lines (a last line without
+// newline is ignored); `v x y z`, `vn x y z`, `vt u v` (v flipped, unused here); `f` with v/vt/vn corner triples, a 4th
+// corner splits the quad into (x, y, z), (z, ext, x) (l.201-208); indices are 1-based in the file.
+// MeshData::setup (src/memory/resources/mesh_data.cc:384-406): vertices are re-indexed in first-appearance order of the
+// unique (v, vt, vn) triples over the corner list; vertex j takes position[v] and normal[vn]. One root per vertex
+// (src/fx/hair.cc:58). A scalp without normals would get per-corner normals from recalculateNormals
+// (src/utils/raw_mesh_file.cc:11-50) and 3 strands per face; that path is not restated: BH_ERR_UNSUPPORTED.
+int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nvertices, int32_t** tri, int64_t* nfaces) {
+  if (!path || !pos3 || !nrm3 || !nvertices || !tri || !nfaces) return BH_ERR_INVALID;
+  *pos3 = *nrm3 = nullptr; *tri = nullptr; *nvertices = *nfaces = 0;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return BH_ERR_INVALID;                                           // "The scalp mesh resource was not found." (hair.cc:45-48)
+  std::string text;
+  char buf[1 << 16];
+  for (size_t n; (n = std::fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, n);
+  std::fclose(f);
+
+  struct V3 { float x, y, z; };
+  struct I3 { int v, t, n; };
+  std::vector<V3> positions, normals;
+  size_t ntex = 0;
+  std::vector<I3> corners;
+  size_t start = 0;
+  for (size_t end; (end = text.find('\n', start)) != std::string::npos; start = end + 1) {
+    text[end] = '\0';
+    const char* s = text.c_str() + start;
+    if (s[0] & 1) continue;                                                // '#', 'o', 'g', 's', 'u'semtl, 'm'tllib: first char odd
+    if (s[0] == 'v') {
+      V3 v{ 0.f, 0.f, 0.f };
+      if (s[1] == ' ') { std::sscanf(s + 2, "%f %f %f", &v.x, &v.y, &v.z); positions.push_back(v); }
+      else if (s[1] == 't') { ++ntex; }
+      else { std::sscanf(s + 3, "%f %f %f", &v.x, &v.y, &v.z); normals.push_back(v); }
+    } else if (s[0] == 'f') {
+      I3 a{ 0, 0, 0 }, b{ 0, 0, 0 }, c{ 0, 0, 0 }, e{ 0, 0, 0 };
+      const bool has_t = ntex != 0, has_n = !normals.empty();
+      if (has_t && has_n) std::sscanf(s + 2, "%d/%d/%d %d/%d/%d %d/%d/%d %d/%d/%d", &a.v, &a.t, &a.n, &b.v, &b.t, &b.n, &c.v, &c.t, &c.n, &e.v, &e.t, &e.n);
+      else if (has_t) std::sscanf(s + 2, "%d/%d %d/%d %d/%d %d/%d", &a.v, &a.t, &b.v, &b.t, &c.v, &c.t, &e.v, &e.t);
+      else if (has_n) std::sscanf(s + 2, "%d//%d %d//%d %d//%d %d//%d", &a.v, &a.n, &b.v, &b.n, &c.v, &c.n, &e.v, &e.n);
+      else std::sscanf(s + 2, "%d %d %d %d", &a.v, &b.v, &c.v, &e.v);
+      corners.push_back(a); corners.push_back(b); corners.push_back(c);
+      if (e.v > 0) { corners.push_back(c); corners.push_back(e); corners.push_back(a); }
+    }
+  }
+  if (corners.empty() || positions.empty()) return BH_ERR_INVALID;
+  if (normals.empty()) return BH_ERR_UNSUPPORTED;
+  std::map<std::tuple<int, int, int>, int32_t> seen;
+  std::vector<I3> unique;
+  std::vector<int32_t> indices;
+  indices.reserve(corners.size());
+  for (const I3& c0 : corners) {
+    const I3 c{ c0.v - 1, c0.t - 1, c0.n - 1 };                            // [1, n] -> [0, n-1]; absent attributes become -1
+    if (c.v < 0 || (size_t)c.v >= positions.size() || c.n < 0 || (size_t)c.n >= normals.size()) return BH_ERR_INVALID;
+    auto key = std::make_tuple(c.v, c.t, c.n);
+    auto it = seen.find(key);
+    if (it == seen.end()) { it = seen.emplace(key, (int32_t)unique.size()).first; unique.push_back(c); }
+    indices.push_back(it->second);
+  }
+  const size_t nv = unique.size(), nf = indices.size() / 3;
+  float* P = static_cast<float*>(std::malloc(sizeof(float) * 3 * nv));
+  float* Nn = static_cast<float*>(std::malloc(sizeof(float) * 3 * nv));
+  int32_t* T = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * 3 * nf));
+  if (!P || !Nn || !T) { std::free(P); std::free(Nn); std::free(T); return BH_ERR_INVALID; }
+  for (size_t j = 0; j < nv; ++j) {
+    const V3 &p = positions[unique[j].v], &n = normals[unique[j].n];
+    P[3 * j] = p.x; P[3 * j + 1] = p.y; P[3 * j + 2] = p.z;
+    Nn[3 * j] = n.x; Nn[3 * j + 1] = n.y; Nn[3 * j + 2] = n.z;
+  }
+  std::memcpy(T, indices.data(), sizeof(int32_t) * 3 * nf);
+  *pos3 = P; *nrm3 = Nn; *tri = T; *nvertices = (int64_t)nv; *nfaces = (int64_t)nf;
+  return BH_OK;
+}
+
+void bh_free(void* ptr) { std::free(ptr); }
 
 }  // extern "C"

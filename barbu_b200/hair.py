@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
-    "bh_sphere_scalp_triangles", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
+    "bh_sphere_scalp_triangles", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
     "bh_host_free", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
 )
@@ -90,6 +90,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_init_tangents_host": ([vp, i64, i64, i64, C.c_int, f32, vp], C.c_int),
         "bh_sphere_scalp_triangles": ([C.c_int, C.c_int, vp], C.c_int),
         "bh_build_patch_indices": ([vp, i64, C.c_int, vp, C.c_int], C.c_int),
+        "bh_load_obj_scalp": ([C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)], C.c_int),
+        "bh_free": ([vp], None),
         "bh_step": ([vp, f32, C.c_int], C.c_int),
         "bh_step_host": ([vp, f32, C.c_int, vp, vp], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
@@ -337,6 +339,24 @@ class ScalpMesh:
         return int(np.asarray(self.indices).reshape(-1, 3).shape[0])
 
 
+def load_obj_scalp(path: str) -> "ScalpMesh":
+    """Scalp MeshData from a Wavefront OBJ, read by the reference's rules (bh_load_obj_scalp)."""
+    lib = load_library()
+    pos, nrm, tri = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nv, nf = C.c_int64(), C.c_int64()
+    rc = lib.bh_load_obj_scalp(os.fsencode(path), C.byref(pos), C.byref(nrm), C.byref(nv), C.byref(tri), C.byref(nf))
+    if rc != BH_OK:
+        raise BarbuHairError(rc, f"cannot load scalp {path!r}")
+    try:
+        P = np.ctypeslib.as_array(C.cast(pos, C.POINTER(C.c_float)), shape=(nv.value, 3)).copy()
+        Nn = np.ctypeslib.as_array(C.cast(nrm, C.POINTER(C.c_float)), shape=(nv.value, 3)).copy()
+        T = np.ctypeslib.as_array(C.cast(tri, C.POINTER(C.c_int32)), shape=(nf.value, 3)).copy()
+    finally:
+        for ptr in (pos, nrm, tri):
+            lib.bh_free(ptr)
+    return ScalpMesh(P, Nn, T)
+
+
 class Hair:
     """Same call surface as the reference's `class Hair` for the simulation path.
 
@@ -375,7 +395,13 @@ class Hair:
     def initialized(self) -> bool:
         return self.nroots != 0
 
-    def setup(self, scalp: Optional[ScalpMesh]):
+    def setup(self, scalp):
+        """`scalp`: a ScalpMesh, or the path of an OBJ scalp resource as in Application.cc:38-39."""
+        if isinstance(scalp, (str, os.PathLike)):
+            try:
+                scalp = load_obj_scalp(os.fspath(scalp))
+            except BarbuHairError:
+                scalp = None
         if scalp is None or scalp.nvertices == 0:
             self.log.append("The scalp mesh resource was not found.")       # hair.cc:45-48
             return

@@ -103,6 +103,14 @@ int  bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first,
 /* Triangle list of the synthetic sphere scalp: 2*(rows-1)*cols triangles, int32 x 3. */
 int  bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri_indices);
 
+/* ---- scalp input: the reference's OBJ reading rules (mesh_data_manager.cc:69-223) and vertex re-indexing
+ * (mesh_data.cc:384-406): one root per unique (v, vt, vn) corner triple in first-appearance order, quads split as
+ * (x, y, z), (z, w, x). Outputs are malloc'ed: release each with bh_free. A file without `vn` lines is refused with
+ * BH_ERR_UNSUPPORTED (the reference would synthesise per-corner normals). Host only, no device needed. */
+int  bh_load_obj_scalp(const char* path, float** root_pos3, float** root_nrm3, int64_t* nvertices,
+                       int32_t** tri_indices, int64_t* nfaces);
+void bh_free(void* ptr);
+
 /* ---- Hair::init_mesh element buffer (hair.cc:397-409), computed on the device --------------- */
 /* out: 6 * nfaces * (nverts-1) int32, host memory. */
 int  bh_build_patch_indices(const int32_t* tri_indices, int64_t nfaces, int nverts, int32_t* out, int device);

@@ -98,6 +98,18 @@ class Hair {
     params_.readonly.nControlPoints = N;
   }
 
+  /* Same from a scalp resource on disk (Application.cc:38-39 passes "models/InfiniteScan/Head_scalp.obj"): read by the
+   * reference's OBJ rules; a missing or unusable file logs and leaves the module uninitialised. */
+  void setup(const char* scalp_obj_path) {
+    float *pos = nullptr, *nrm = nullptr; std::int32_t* tri = nullptr;
+    ScalpMesh scalp;
+    if (scalp_obj_path && bh_load_obj_scalp(scalp_obj_path, &pos, &nrm, &scalp.nvertices, &tri, &scalp.nfaces) == BH_OK) {
+      scalp.positions = pos; scalp.normals = nrm; scalp.indices = tri;
+    }
+    setup(scalp);
+    bh_free(pos); bh_free(nrm); bh_free(tri);
+  }
+
   /* One simulation step (hair.cc:89-125). */
   void update(float const dt) {
     if (!initialized()) {

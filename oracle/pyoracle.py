@@ -180,3 +180,47 @@ def ref_patch_indices(tri, nstrands: int, nverts: int) -> np.ndarray:
 
 def ref_simplex2(x: float, y: float) -> float:
     return float(_ref("host", 4).ref_host_simplex2(x, y))
+
+
+# ---- scalp input ----------------------------------------------------------------------------------
+
+def obj_scalp(path: str):
+    """Plain-Python restatement of how the reference reads an OBJ scalp (small files only):
+    ParseOBJ, src/memory/resources/mesh_data_manager.cc:69-223 — '\\n'-terminated lines; lines whose first byte is odd
+    ('#', 'o', 'g', 's', 'u', 'm') carry no geometry; `v`, `vn`; `f` corners v/vt/vn, quads split (x, y, z), (z, w, x);
+    MeshData::setup, src/memory/resources/mesh_data.cc:384-406 — vertices = unique (v, vt, vn) triples in
+    first-appearance order. Returns (positions (S,3) f32, normals (S,3) f32, triangles (F,3) i32)."""
+    raw = open(path, "rb").read().decode("latin-1")
+    lines = raw.split("\n")[:-1]                       # a last line without '\n' is never reached by the strchr loop
+    pos, nrm, ntex, corners = [], [], 0, []
+    for s in lines:
+        if not s or (ord(s[0]) & 1):
+            continue
+        if s[0] == "v":
+            if s[1] == " ":
+                pos.append([np.float32(x) for x in s[2:].split()[:3]])
+            elif s[1] == "t":
+                ntex += 1
+            else:
+                nrm.append([np.float32(x) for x in s[3:].split()[:3]])
+        elif s[0] == "f":
+            cs = []
+            for tok in s[2:].split()[:4]:
+                parts = tok.split("/")
+                v = int(parts[0])
+                t = int(parts[1]) if len(parts) > 1 and parts[1] else 0
+                n = int(parts[2]) if len(parts) > 2 and parts[2] else 0
+                cs.append((v, t, n))
+            corners += cs[:3]
+            if len(cs) == 4 and cs[3][0] > 0:
+                corners += [cs[2], cs[3], cs[0]]
+    seen, uniq, idx = {}, [], []
+    for v, t, n in corners:
+        key = (v - 1, t - 1, n - 1)
+        if key not in seen:
+            seen[key] = len(uniq)
+            uniq.append(key)
+        idx.append(seen[key])
+    P = np.array([pos[k[0]] for k in uniq], np.float32).reshape(-1, 3)
+    Nn = np.array([nrm[k[2]] for k in uniq], np.float32).reshape(-1, 3)
+    return P, Nn, np.array(idx, np.int32).reshape(-1, 3)
