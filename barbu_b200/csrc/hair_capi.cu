@@ -67,6 +67,11 @@ struct bh_sim {
   float* skin_weights3 = nullptr;
   float* skin_dq = nullptr;
   int skin_dq_cap = 0;
+  // tess-stream stage
+  int* tess_patch = nullptr;            // device copy of the patch element buffer
+  int64_t tess_npatches = 0;
+  float4* tess_out = nullptr;           // GL_LINES vertex stream (xyz, relPos)
+  int64_t tess_out_cap = 0, tess_out_count = 0;
   // GL interop
   cudaGraphicsResource* gl_resource = nullptr;
 };
@@ -181,6 +186,7 @@ int bh_destroy(bh_sim* s) {
   DeviceGuard g(s->device);
   if (s->gl_resource) cudaGraphicsUnregisterResource(s->gl_resource);
   cudaFree(s->buffer0); cudaFree(s->tile_counters); cudaFree(s->root_pos3); cudaFree(s->root_nrm3);
+  cudaFree(s->tess_patch); cudaFree(s->tess_out);
   cudaFree(s->skin_rest3); cudaFree(s->skin_joints4); cudaFree(s->skin_weights3); cudaFree(s->skin_dq);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
@@ -472,6 +478,56 @@ int bh_skin_roots(bh_sim* s, const float* dq_palette, int njoints) {
   rc = unmap_gl(s); if (rc) return rc;
   // the palette is pageable host memory owned by the caller: do not return before it was consumed
   BH_CUDA(cudaStreamSynchronize(s->stream));
+  return BH_OK;
+}
+
+int bh_tess_set_patches(bh_sim* s, const int32_t* patch_indices, int64_t nelems) {
+  if (!s || !patch_indices || nelems <= 0 || nelems % 6 != 0) return fail(BH_ERR_INVALID, "bh_tess_set_patches: need 6 indices per patch");
+  for (int64_t q = 0; q < nelems; ++q)
+    if (patch_indices[q] < 0 || patch_indices[q] >= s->nvertices) return fail(BH_ERR_INVALID, "bh_tess_set_patches: index outside the vertex range");
+  DeviceGuard g(s->device);
+  cudaFree(s->tess_patch); s->tess_patch = nullptr; s->tess_npatches = 0;
+  BH_CUDA(cudaMalloc(&s->tess_patch, sizeof(int) * (size_t)nelems));
+  BH_CUDA(cudaMemcpyAsync(s->tess_patch, patch_indices, sizeof(int) * (size_t)nelems, cudaMemcpyHostToDevice, s->stream));
+  BH_CUDA(cudaStreamSynchronize(s->stream));
+  s->tess_npatches = nelems / 6;
+  return BH_OK;
+}
+
+int64_t bh_tess_stream_count(const bh_sim* s, const bh_tess_params* t) {
+  if (!s || !t || t->ninstances < 1 || t->nlines < 1 || t->nsubsegments < 1) return -1;
+  return s->tess_npatches * t->ninstances * t->nlines * t->nsubsegments * 2;
+}
+
+int bh_tess_stream(bh_sim* s, const bh_tess_params* t, float* out4_host) {
+  if (!s || !t) return fail(BH_ERR_INVALID, "bh_tess_stream: NULL argument");
+  if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_tess_stream: no strand state");
+  if (!s->tess_patch) return fail(BH_ERR_NOT_INITIALIZED, "bh_tess_stream: call bh_tess_set_patches first");
+  const int64_t count = bh_tess_stream_count(s, t);
+  if (count < 0) return fail(BH_ERR_INVALID, "bh_tess_stream: ninstances, nlines and nsubsegments must be >= 1");
+  DeviceGuard g(s->device);
+  if (count > s->tess_out_cap) {
+    cudaFree(s->tess_out); s->tess_out = nullptr; s->tess_out_cap = 0;
+    BH_CUDA(cudaMalloc(&s->tess_out, sizeof(float4) * (size_t)count));
+    s->tess_out_cap = count;
+  }
+  int rc = map_gl(s); if (rc) return rc;
+  BH_CUDA(bh::launch_tess_stream(s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_TANGENT], s->tess_patch, s->tess_npatches, s->nverts,
+                                 s->params.scale, t->ninstances, t->nlines, t->nsubsegments, t->seed, s->tess_out, s->stream));
+  s->launches += 1;
+  s->tess_out_count = count;
+  rc = unmap_gl(s); if (rc) return rc;
+  if (out4_host) {
+    BH_CUDA(cudaMemcpyAsync(out4_host, s->tess_out, sizeof(float4) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    BH_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  return BH_OK;
+}
+
+int bh_tess_device_buffer(bh_sim* s, void** device_ptr, int64_t* count) {
+  if (!s || !device_ptr) return fail(BH_ERR_INVALID, "bh_tess_device_buffer: NULL argument");
+  *device_ptr = s->tess_out;
+  if (count) *count = s->tess_out_count;
   return BH_OK;
 }
 

@@ -13,4 +13,8 @@ cudaError_t launch_patch_indices(const int* tri, long long nfaces, int nverts, i
 cudaError_t launch_skin_roots_dq(const float* rest_pos3, const int* joints4, const float* weights3, const float* dq,
                                  long long nstrands, int nverts, float4* pos, cudaStream_t stream);
 
+// hair_tess.cu: tess-stream stage; out holds npatches * ninstances * nlines * nsub * 2 float4
+cudaError_t launch_tess_stream(const float4* pos, const float4* tan, const int* patch, long long npatches, int nverts, float scale,
+                               int ninstances, int nlines, int nsub, unsigned seed, float4* out, cudaStream_t stream);
+
 }  // namespace bh

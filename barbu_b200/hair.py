@@ -29,13 +29,17 @@ ABI_SYMBOLS = (
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
     "bh_sphere_scalp_triangles", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
-    "bh_host_free", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
+    "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
 )
 
 
 class BhCapsule(C.Structure):
     _fields_ = [("a", C.c_float * 3), ("b", C.c_float * 3), ("radius", C.c_float)]
+
+
+class BhTessParams(C.Structure):
+    _fields_ = [("ninstances", C.c_int), ("nlines", C.c_int), ("nsubsegments", C.c_int), ("seed", C.c_uint)]
 
 
 class BhParams(C.Structure):
@@ -96,6 +100,10 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_step_host": ([vp, f32, C.c_int, vp, vp], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
+        "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
+        "bh_tess_stream_count": ([vp, C.POINTER(BhTessParams)], i64),
+        "bh_tess_stream": ([vp, C.POINTER(BhTessParams), vp], C.c_int),
+        "bh_tess_device_buffer": ([vp, C.POINTER(vp), C.POINTER(i64)], C.c_int),
         "bh_launch_count": ([vp], i64),
         "bh_step_kernel_kind": ([vp], C.c_int),
         "bh_selftest_math": ([C.c_int, C.POINTER(C.c_uint64)], C.c_int),
@@ -305,6 +313,21 @@ class HairSim:
     def kernel_kind(self) -> int:
         """0 streaming, 1 per-strand pipelined, 2 generic (bh_step_kernel_kind)."""
         return int(self._lib.bh_step_kernel_kind(self._h))
+
+    # -- next stage: tess-stream ---------------------------------------------------------------
+    def tess_set_patches(self, patch_indices):
+        idx = np.ascontiguousarray(patch_indices, dtype=np.int32).reshape(-1)
+        _check(self._lib.bh_tess_set_patches(self._h, _ptr(idx), idx.size))
+
+    def tess_stream(self, ninstances: int = 3, nlines: int = 2, nsubsegments: int = 16, seed: int = 0, download: bool = True):
+        """GL_LINES vertex stream (count, 4) of the interpolated render strands (defaults: hair.h:33-35)."""
+        t = BhTessParams(ninstances, nlines, nsubsegments, seed)
+        n = self._lib.bh_tess_stream_count(self._h, C.byref(t))
+        if n < 0:
+            raise ValueError("ninstances, nlines and nsubsegments must be >= 1")
+        out = np.empty((n, 4), np.float32) if download else None
+        _check(self._lib.bh_tess_stream(self._h, C.byref(t), _ptr(out)))
+        return out if download else n
 
     # -- extensions --------------------------------------------------------------------------
     def set_skin(self, rest_root_pos3, joints4, weights3):

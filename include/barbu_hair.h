@@ -137,6 +137,18 @@ int  bh_selftest_math(int device, uint64_t* mismatches);
 int  bh_set_skin(bh_sim* sim, const float* rest_root_pos3, const int32_t* joints4, const float* weights3);
 int  bh_skin_roots(bh_sim* sim, const float* dq_palette, int njoints);
 
+/* ---- next stage: the tess-stream pass of Hair::render (hair.cc:141-173) on the device ------------ */
+/* Interpolated render strands as the GL_LINES vertex stream (xyz, relPos) that glDrawTransformFeedback consumes:
+ * per patch (6 control points, bh_build_patch_indices order), instance, isoline and sub-segment two float4.
+ * Formulas of shaders/hair/02_tess_stream/*.glsl + shared/inc_maths.glsl (hermite_mix, sample_triangle2, smoothstep2);
+ * tess coordinates, primitive order and the (seeded, counter-based) random pair are defined by this library because
+ * the reference leaves them to the GL implementation / to std::random_device: no reference parity is claimed there. */
+typedef struct bh_tess_params { int ninstances; int nlines; int nsubsegments; unsigned seed; } bh_tess_params;   /* hair.h:32-36 */
+int     bh_tess_set_patches(bh_sim* sim, const int32_t* patch_indices, int64_t nelems);   /* upload once per scalp */
+int64_t bh_tess_stream_count(const bh_sim* sim, const bh_tess_params* t);                  /* float4 per call, -1 on bad params */
+int     bh_tess_stream(bh_sim* sim, const bh_tess_params* t, float* out4_host /* NULL: leave it on the device */);
+int     bh_tess_device_buffer(bh_sim* sim, void** device_ptr, int64_t* count);
+
 /* ---- CUDA-GL interop on buffer 0 (pbuffer_.read_ssbo_id(), hair.cc:371) --------------------- */
 /* cudaGraphicsGLRegisterBuffer; while registered, bh_step maps the GL buffer, steps in place and
  * unmaps, so the render VAO (hair.cc:371-389) sees the new positions without a copy. Needs a

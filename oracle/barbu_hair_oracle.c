@@ -377,3 +377,83 @@ uint64_t bho_fnv1a64(const void* data, uint64_t n) {
   for (uint64_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
   return h;
 }
+
+/* ---- tess-stream stage: the consumer right after the simulation -------------------------
+ * Restates, per output vertex, what the reference's VS -> TCS -> TES -> GS transform-feedback pass computes
+ * (src/shaders/hair/02_tess_stream/*.glsl; draw call src/fx/hair.cc:141-173):
+ *   patch = 6 control points (3 master strands x the two ends of one segment, hair.cc:397-409);
+ *   TCS  tangents *= uScaleFactor (tcs_stream_hair.glsl:41); isolines: outer[0] = nlines, outer[1] = nsubsegments;
+ *   TES  p_k = hermite_mix(P[2k], P[2k+1], T[2k], T[2k+1], x)   (tes:33-35, shared/inc_maths.glsl:210-228)
+ *        position = sample_triangle2(p0, p1, p2, rand.xy)        (tes:59-60, inc_maths.glsl:107-115)
+ *        relPos   = smoothstep2(0, 1, relPos(first CP) + x / N)  (tes:63-64, inc_maths.glsl:239-241,263-266;
+ *                                                                 vs_stream_hair.glsl:24: (gl_VertexID % N) / float(N))
+ *   GS   each isoline segment leaves as two vec4 (position.xyz, relPos) (gs_stream_hair.glsl:21-29), GL_LINES.
+ * Defined here because the reference leaves it to the implementation (no reference parity is claimed for them):
+ *   - isoline tess coordinates: x = k / nsubsegments (k = 0..nsubsegments), y = line / nlines (equal_spacing ideal);
+ *   - primitive order: instance-major, then patch, line, segment;
+ *   - vector arithmetic order as GLM evaluates the same expressions (dot4 = (x*x' + y*y') + (z*z' + w*w'),
+ *     vec * mat = per-column dot, mat3x4 * vec3 = (m0*v.x + m1*v.y) + m2*v.z);
+ *   - the random pair: the reference indexes a std430 `vec3[]` view of 4096 mt19937(random_device) floats with
+ *     int(y*40 + instance) % 4096 (tes:52-54), reading out of bounds past element 1023 (SURVEY §8 a-ext). Kept: the index
+ *     formula; replaced: the table, by the counter-based hash below (seeded, reproducible, no out-of-bounds). */
+static uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+static float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+void bho_tess_random_pair(uint32_t seed, int index, float st[2]) {
+  st[0] = u01(lowbias32(seed + 0x9E3779B9u * (uint32_t)(2 * index + 1)));
+  st[1] = u01(lowbias32(seed + 0x9E3779B9u * (uint32_t)(2 * index + 2)));
+}
+static inline float dot4(const float a[4], const float b[4]) { return (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]); }
+/* hermite_mix: vU * mHermit * B, xyz only (w = h0 + h1 is dropped by the TES) */
+static void hermite3(const float p0[3], const float p1[3], const float t0[3], const float t1[3], float u, float out[3]) {
+  static const float M[4][4] = { { 2.0f, -3.0f, 0.0f, 1.0f }, { -2.0f, 3.0f, 0.0f, 0.0f }, { 1.0f, -2.0f, 1.0f, 0.0f }, { 1.0f, -1.0f, 0.0f, 0.0f } };
+  const float vU[4] = { u * u * u, u * u, u, 1.0f };
+  const float h[4] = { dot4(vU, M[0]), dot4(vU, M[1]), dot4(vU, M[2]), dot4(vU, M[3]) };
+  for (int c = 0; c < 3; ++c) {
+    const float col[4] = { p0[c], p1[c], t0[c], t1[c] };
+    out[c] = dot4(h, col);
+  }
+}
+int64_t bho_tess_stream_count(int64_t npatches, int ninstances, int nlines, int nsubsegments) {
+  return npatches * ninstances * nlines * nsubsegments * 2;
+}
+void bho_tess_stream(const float* pos4, const float* tan4, const int32_t* patch_indices, int64_t npatches, int nverts,
+                     float scale, int ninstances, int nlines, int nsubsegments, uint32_t seed, float* out4) {
+  const float invN = 1.0f;  (void)invN;
+  for (int inst = 0; inst < ninstances; ++inst)
+    for (int64_t pa = 0; pa < npatches; ++pa) {
+      const int32_t* e = patch_indices + 6 * pa;
+      float P[6][3], T[6][3];
+      for (int k = 0; k < 6; ++k)
+        for (int c = 0; c < 3; ++c) { P[k][c] = pos4[4 * (int64_t)e[k] + c]; T[k][c] = tan4[4 * (int64_t)e[k] + c] * scale; }
+      const float rel0 = (float)(e[0] % nverts) / (float)nverts;
+      for (int line = 0; line < nlines; ++line) {
+        const float y = (float)line / (float)nlines;
+        float st[2];
+        bho_tess_random_pair(seed, (int)(y * 40.0f + (float)inst) % 4096, st);
+        if (st[0] + st[1] > 1.0f) {                       /* sample_triangle2 */
+          st[0] = fmaxf(st[0], st[1]);
+          st[1] = fminf(st[0], st[1]);
+          st[0] = 1.0f - st[0];
+        }
+        const float cz = 1.0f - (st[0] + st[1]);
+        float pts[3];
+        for (int k = 0; k <= nsubsegments; ++k) {
+          const float x = (float)k / (float)nsubsegments;
+          float q0[3], q1[3], q2[3];
+          hermite3(P[0], P[1], T[0], T[1], x, q0);
+          hermite3(P[2], P[3], T[2], T[3], x, q1);
+          hermite3(P[4], P[5], T[4], T[5], x, q2);
+          for (int c = 0; c < 3; ++c) pts[c] = (q0[c] * st[0] + q1[c] * st[1]) + q2[c] * cz;
+          float t = (rel0 + x / (float)nverts - 0.0f) / (1.0f - 0.0f);
+          t = fminf(fmaxf(t, 0.0f), 1.0f);
+          const float rel = t * t * t * (10.0f + t * (-15.0f + 6.0f * t));
+          const int64_t base = ((((int64_t)inst * npatches + pa) * nlines + line) * nsubsegments) * 2;
+          if (k < nsubsegments) { float* o = out4 + 4 * (base + 2 * k); o[0] = pts[0]; o[1] = pts[1]; o[2] = pts[2]; o[3] = rel; }
+          if (k > 0) { float* o = out4 + 4 * (base + 2 * (k - 1) + 1); o[0] = pts[0]; o[1] = pts[1]; o[2] = pts[2]; o[3] = rel; }
+        }
+      }
+    }
+}

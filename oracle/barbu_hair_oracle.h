@@ -89,6 +89,14 @@ void bho_skin_roots_dq(const float* rest_pos3, const float* rest_nrm3, const int
 /* FNV-1a 64 over raw bytes — "checksum of checksums" helper for full-size property tests. */
 uint64_t bho_fnv1a64(const void* data, uint64_t nbytes);
 
+/* Tess-stream stage (src/shaders/hair/02_tess_stream, hair.cc:141-173): interpolated render strands as GL_LINES
+ * vertices (xyz, relPos). out4: bho_tess_stream_count(...) float4. See the .c file for what is reference text and what
+ * is defined here (tess coordinates, primitive order, the seeded random pair). */
+void bho_tess_random_pair(uint32_t seed, int index, float st[2]);
+int64_t bho_tess_stream_count(int64_t npatches, int ninstances, int nlines, int nsubsegments);
+void bho_tess_stream(const float* pos4, const float* tan4, const int32_t* patch_indices, int64_t npatches, int nverts,
+                     float scale, int ninstances, int nlines, int nsubsegments, uint32_t seed, float* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,6 +182,20 @@ def ref_simplex2(x: float, y: float) -> float:
     return float(_ref("host", 4).ref_host_simplex2(x, y))
 
 
+def tess_stream(pos4, tan4, patch, nverts: int, scale: float, ninstances: int, nlines: int, nsubsegments: int, seed: int):
+    """Interpolated render strands of the tess-stream stage: (count, 4) float32 GL_LINES vertices (xyz, relPos)."""
+    patch = np.ascontiguousarray(patch, np.int32)
+    npatches = patch.size // 6
+    lib = oracle()
+    lib.bho_tess_stream_count.restype = C.c_int64
+    n = lib.bho_tess_stream_count(C.c_int64(npatches), C.c_int(ninstances), C.c_int(nlines), C.c_int(nsubsegments))
+    out = np.empty((n, 4), np.float32)
+    lib.bho_tess_stream(_p(np.ascontiguousarray(pos4, np.float32)), _p(np.ascontiguousarray(tan4, np.float32)), _p(patch),
+                        C.c_int64(npatches), C.c_int(nverts), C.c_float(scale), C.c_int(ninstances), C.c_int(nlines),
+                        C.c_int(nsubsegments), C.c_uint32(seed), _p(out))
+    return out
+
+
 # ---- scalp input ----------------------------------------------------------------------------------
 
 def obj_scalp(path: str):
