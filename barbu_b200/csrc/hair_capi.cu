@@ -3,8 +3,6 @@
 // Host-side counterpart of Hair::{setup, update, set_bounding_sphere} (src/fx/hair.cc:42-125) and of
 // PingPongBuffer (src/memory/pingpong_buffer.cc): one device allocation holding the three SoA float4
 // planes of "buffer 0", updated in place. No CPU fallback: every path below ends in a CUDA call.
-#include "../../include/barbu_hair.h"
-
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -22,71 +20,27 @@
 extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource, unsigned int buffer,
                                                     unsigned int flags);
 
+#include "hair_sim.cuh"
+
 namespace {
-
 thread_local std::string g_last_error;
+}  // namespace
 
-int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+namespace bh {
+int fail(int code, const char* what, cudaError_t e) {
   char buf[512];
   if (e != cudaSuccess) std::snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   else std::snprintf(buf, sizeof buf, "%s", what);
   g_last_error = buf;
   return code;
 }
+}  // namespace bh
 
-#define BH_CUDA(expr)                                                       \
-  do {                                                                      \
-    cudaError_t e__ = (expr);                                               \
-    if (e__ != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, #expr, e__); } \
-  } while (0)
-
-constexpr int kHostPipeStreams = 4;
-
-}  // namespace
-
-struct bh_sim {
-  int device = 0;
-  int64_t nstrands = 0;
-  int nverts = 0;
-  int64_t nvertices = 0;                 // V = S * N
-  float4* buffer0 = nullptr;             // 3 planes, layout of PingPongBuffer buffer 0
-  float4* planes[BH_NUM_PLANES] = { nullptr, nullptr, nullptr };
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaStream_t pipe[kHostPipeStreams] = { nullptr, nullptr, nullptr, nullptr };
-  bh_params params;
-  bool initialized = false;              // Hair::initialized(): state present
-  int64_t launches = 0;
-  unsigned int* tile_counters = nullptr;  // kHostPipeStreams + 1 words: one tile scheduler per stream that may be in flight
-  // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)
-  float* root_pos3 = nullptr;
-  float* root_nrm3 = nullptr;
-  // skinning extension
-  float* skin_rest3 = nullptr;
-  int* skin_joints4 = nullptr;
-  float* skin_weights3 = nullptr;
-  float* skin_dq = nullptr;
-  int skin_dq_cap = 0;
-  // tess-stream stage
-  int* tess_patch = nullptr;            // device copy of the patch element buffer
-  int64_t tess_npatches = 0;
-  float4* tess_out = nullptr;           // GL_LINES vertex stream (xyz, relPos)
-  int64_t tess_out_cap = 0, tess_out_count = 0;
-  // GL interop
-  cudaGraphicsResource* gl_resource = nullptr;
-};
+using bh::fail;
+using bh::DeviceGuard;
+using bh::kHostPipeStreams;
 
 namespace {
-
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
-    if (cudaSetDevice(dev) != cudaSuccess) ok = false;
-  }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 bh::StepArgs make_args(const bh_sim* s, float dt, float4* pos, float4* vel, int64_t nstrands) {
   const bh_params& p = s->params;
@@ -118,6 +72,9 @@ int ensure_roots(bh_sim* s) {
   return BH_OK;
 }
 
+}  // namespace
+
+namespace bh {
 int map_gl(bh_sim* s) {
   if (!s->gl_resource) return BH_OK;
   BH_CUDA(cudaGraphicsMapResources(1, &s->gl_resource, s->stream));
@@ -133,7 +90,9 @@ int unmap_gl(bh_sim* s) {
   return BH_OK;
 }
 
-}  // namespace
+}  // namespace bh
+using bh::map_gl;
+using bh::unmap_gl;
 
 extern "C" {
 
@@ -186,7 +145,7 @@ int bh_destroy(bh_sim* s) {
   DeviceGuard g(s->device);
   if (s->gl_resource) cudaGraphicsUnregisterResource(s->gl_resource);
   cudaFree(s->buffer0); cudaFree(s->tile_counters); cudaFree(s->root_pos3); cudaFree(s->root_nrm3);
-  cudaFree(s->tess_patch); cudaFree(s->tess_out);
+  cudaFree(s->tess_patch); cudaFree(s->tess_out); cudaFree(s->checksum_words);
   cudaFree(s->skin_rest3); cudaFree(s->skin_joints4); cudaFree(s->skin_weights3); cudaFree(s->skin_dq);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);

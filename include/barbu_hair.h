@@ -149,6 +149,41 @@ int64_t bh_tess_stream_count(const bh_sim* sim, const bh_tess_params* t);       
 int     bh_tess_stream(bh_sim* sim, const bh_tess_params* t, float* out4_host /* NULL: leave it on the device */);
 int     bh_tess_device_buffer(bh_sim* sim, void** device_ptr, int64_t* count);
 
+/* ---- next stage: strand-state files and device checksums -------------------------------------------- */
+/* The reference has no persistence (state lives in GL buffers, regenerated from rand() at start-up, hair.cc:236-361).
+ * A state file is the planes of buffer 0, byte for byte in PingPongBuffer order (pingpong_buffer.cc:16-17,44-48), behind
+ * a 512-byte little-endian header:
+ *     0  char[8] "BARBUHS1"      8  u32 version (1)      12  u32 header_bytes (512)
+ *    16  i64 nstrands (this file)                        24  i32 nverts       28  u32 plane_mask (bit p: plane p stored)
+ *    32  i64 total_strands       40  i64 first_strand (shard coordinates)        48  i64 frame
+ *    56  f32 dt                  60  u32 seed (srand seed of the length jitter, hair.cc:273-275)
+ *    64  u64 checksum[2]         80  u32 params_bytes (292)   84  u32 reserved   88  bh_params   ...zero padding to 512
+ *   512  the stored planes in ascending order, nstrands * nverts * 16 bytes each
+ * checksum (computed on the device, one streaming pass): over the 32-bit words w of the stored planes, with
+ * key = (plane << 60) + 4 * global_vertex + component and G = 0x9E3779B97F4A7C15:
+ *     checksum[0] = sum w,    checksum[1] = sum w * ((key + 1) * G)          (both mod 2^64)
+ * Keys use GLOBAL vertex indices ((first_strand + strand) * nverts + i), so the checksum of a scalp equals the wrapping
+ * sum of the checksums of its shards. */
+typedef struct bh_state_info {
+  int64_t  nstrands;      /* out */
+  int      nverts;        /* out */
+  unsigned plane_mask;    /* in (0 = all three planes) / out */
+  int64_t  total_strands; /* in (0 = nstrands) / out */
+  int64_t  first_strand;  /* in / out */
+  int64_t  frame;         /* in / out: caller's frame counter */
+  float    dt;            /* in / out: caller's frame time step */
+  unsigned seed;          /* in / out */
+  uint64_t checksum[2];   /* out */
+  bh_params params;       /* out: the sim's parameters when the file was written */
+} bh_state_info;
+int  bh_state_checksum(bh_sim* sim, unsigned plane_mask, int64_t first_strand, uint64_t out[2]);
+int  bh_save_state(bh_sim* sim, const char* path, const bh_state_info* info /* NULL: unsharded, frame 0 */);
+/* Header only; host only (no device needed): learn the shape before bh_create. */
+int  bh_peek_state(const char* path, bh_state_info* info);
+/* The sim must have the file's shape. Loads the stored planes, verifies the checksum on the device
+ * (BH_ERR_INVALID on mismatch: the sim then holds no valid state) and adopts the stored parameters. */
+int  bh_load_state(bh_sim* sim, const char* path, bh_state_info* info /* may be NULL */);
+
 /* ---- CUDA-GL interop on buffer 0 (pbuffer_.read_ssbo_id(), hair.cc:371) --------------------- */
 /* cudaGraphicsGLRegisterBuffer; while registered, bh_step maps the GL buffer, steps in place and
  * unmaps, so the render VAO (hair.cc:371-389) sees the new positions without a copy. Needs a
