@@ -31,6 +31,7 @@ ABI_SYMBOLS = (
     "bh_sphere_scalp_triangles", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
+    "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
 )
 
 
@@ -49,6 +50,15 @@ class BhParams(C.Structure):
         ("gravity", C.c_float * 3), ("force_coeff", C.c_float), ("damp", C.c_float), ("math", C.c_int),
         ("wind", C.c_float * 3), ("drag", C.c_float), ("ncapsules", C.c_int),
         ("capsules", BhCapsule * BH_MAX_CAPSULES),
+    ]
+
+
+class BhStateInfo(C.Structure):
+    """struct bh_state_info of include/barbu_hair.h (header fields of a BARBUHS1 state file)."""
+    _fields_ = [
+        ("nstrands", C.c_int64), ("nverts", C.c_int), ("plane_mask", C.c_uint), ("total_strands", C.c_int64),
+        ("first_strand", C.c_int64), ("frame", C.c_int64), ("dt", C.c_float), ("seed", C.c_uint),
+        ("checksum", C.c_uint64 * 2), ("params", BhParams),
     ]
 
 
@@ -111,6 +121,10 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_skin_roots": ([vp, vp, C.c_int], C.c_int),
         "bh_register_gl_buffer": ([vp, C.c_uint], C.c_int),
         "bh_unregister_gl_buffer": ([vp], C.c_int),
+        "bh_state_checksum": ([vp, C.c_uint, i64, C.POINTER(C.c_uint64)], C.c_int),
+        "bh_save_state": ([vp, C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
+        "bh_peek_state": ([C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
+        "bh_load_state": ([vp, C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
         "bh_last_error": ([], C.c_char_p),
         "bh_version": ([], C.c_char_p),
     }
@@ -148,6 +162,13 @@ def random_values(seed: int, first: int, count: int) -> np.ndarray:
     out = np.empty(count, np.float32)
     _check(load_library().bh_random_values(seed, first, count, _ptr(out)))
     return out
+
+
+def peek_state(path) -> BhStateInfo:
+    """Header of a BARBUHS1 state file (bh_peek_state; host only)."""
+    info = BhStateInfo()
+    _check(load_library().bh_peek_state(os.fsencode(path), C.byref(info)))
+    return info
 
 
 def selftest_math(device: int = 0) -> int:
@@ -294,6 +315,36 @@ class HairSim:
         if r.size != self.nstrands:
             raise ValueError("one jitter value per strand of this shard")
         _check(self._lib.bh_init_sphere_scalp(self._h, rows, cols, first, _ptr(r), maxlength))
+
+    # -- state files / checksums ---------------------------------------------------
+    def checksum(self, plane_mask: int = 7, first_strand: int = 0):
+        """(sum, keyed sum) of the planes in `plane_mask`, computed on the device (bh_state_checksum)."""
+        out = (C.c_uint64 * 2)()
+        _check(self._lib.bh_state_checksum(self._h, plane_mask, first_strand, out))
+        return int(out[0]), int(out[1])
+
+    def save(self, path, *, plane_mask: int = 7, total_strands: int = 0, first_strand: int = 0, frame: int = 0,
+             dt: float = 0.0, seed: int = 0):
+        info = BhStateInfo(plane_mask=plane_mask, total_strands=total_strands, first_strand=first_strand, frame=frame,
+                           dt=dt, seed=seed)
+        _check(self._lib.bh_save_state(self._h, os.fsencode(path), C.byref(info)))
+
+    def load(self, path) -> BhStateInfo:
+        """Load a state file of this sim's shape: planes + parameters; verified by the device checksum."""
+        info = BhStateInfo()
+        _check(self._lib.bh_load_state(self._h, os.fsencode(path), C.byref(info)))
+        return info
+
+    @classmethod
+    def from_state(cls, path, device: int = 0):
+        """bh_peek_state -> bh_create -> bh_load_state. Returns (sim, info)."""
+        head = peek_state(path)
+        sim = cls(head.nstrands, head.nverts, device)
+        try:
+            return sim, sim.load(path)
+        except Exception:
+            sim.close()
+            raise
 
     # -- stepping ----------------------------------------------------------------------------
     def step(self, dt: float, substeps: int = 1):

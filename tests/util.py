@@ -56,3 +56,33 @@ def rel_err(a, b):
     """max over vertices of |a-b| / |b| on xyz (SURVEY.md App. B error measure)."""
     a, b = np.asarray(a, np.float64)[:, :3], np.asarray(b, np.float64)[:, :3]
     return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)
+
+
+def host_checksum(planes, nverts: int, first_strand: int = 0, plane_ids=(0, 1, 2)):
+    """The state checksum include/barbu_hair.h defines, restated with numpy (checker: the product computes it on the device)."""
+    G = np.uint64(0x9E3779B97F4A7C15)
+    c0 = np.uint64(0)
+    c1 = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for pid, plane in zip(plane_ids, planes):
+            w = np.ascontiguousarray(plane, dtype=np.float32).reshape(-1).view(np.uint32).astype(np.uint64)
+            key = (np.uint64(pid) << np.uint64(60)) + np.uint64(4 * first_strand * nverts) + np.arange(w.size, dtype=np.uint64)
+            c0 = c0 + w.sum(dtype=np.uint64)
+            c1 = c1 + (w * ((key + np.uint64(1)) * G)).sum(dtype=np.uint64)
+    return int(c0), int(c1)
+
+
+def write_state_file(path, planes, nstrands, nverts, *, params_bytes, plane_mask=None, total=None, first=0, frame=0, dt=0.0, seed=0,
+                     magic=b"BARBUHS1", version=1, checksum=None):
+    """A BARBUHS1 state file written from the format description in include/barbu_hair.h alone (struct-packed here,
+    independently of the C writer). `planes`: list of (V, 4) float32 in ascending plane order; `params_bytes`: bh_params."""
+    import struct
+    ids = [p for p in range(3) if (plane_mask if plane_mask is not None else (1 << len(planes)) - 1) >> p & 1]
+    mask = sum(1 << p for p in ids)
+    c = checksum if checksum is not None else host_checksum(planes, nverts, first, ids)
+    head = struct.pack("<8sIIqiIqqqfIQQII", magic, version, 512, nstrands, nverts, mask, total if total is not None else nstrands,
+                       first, frame, dt, seed, c[0], c[1], len(params_bytes), 0) + bytes(params_bytes)
+    with open(path, "wb") as f:
+        f.write(head.ljust(512, b"\0"))
+        for pl in planes:
+            f.write(np.ascontiguousarray(pl, np.float32).tobytes())
