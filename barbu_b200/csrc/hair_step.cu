@@ -468,7 +468,15 @@ int step_kernel_kind(const StepArgs& a) {
 
 cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
   if (a.nstrands <= 0 || a.nverts <= 0) return cudaSuccess;
-  if (tile_counter && stream_kernel_eligible(a)) return launch_step_stream(a, math, stream, tile_counter);
+  if (tile_counter && stream_kernel_eligible(a)) {
+    if (a.nverts != 4 || a.nstrands % 2 == 0) return launch_step_stream(a, math, stream, tile_counter);
+    // nverts == 4 pairs strands into 128-byte tensor rows: the last strand of an odd count takes the per-strand kernel
+    StepArgs head = a, tail = a;
+    head.nstrands = a.nstrands - 1;
+    tail.nstrands = 1; tail.pos = a.pos + head.nstrands * 4; tail.vel = a.vel + head.nstrands * 4;
+    const cudaError_t e = launch_step_stream(head, math, stream, tile_counter);
+    return e != cudaSuccess ? e : launch_step(tail, math, stream, nullptr);
+  }
   const bool caps = a.ncaps > 0;
   if (math == 0) return caps ? launch_t<MathExact, true>(a, stream) : launch_t<MathExact, false>(a, stream);
   return caps ? launch_t<MathFast, true>(a, stream) : launch_t<MathFast, false>(a, stream);

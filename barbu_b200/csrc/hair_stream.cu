@@ -170,7 +170,7 @@ struct Pipe {
   V3p P[4];        // C(i, k): input of each stage; valid only after a step with a push-out
   u64 L[4];        // sf * rest_i of the vertex in each stage
   V3 heldd;        // d_i of the vertex waiting for d_{i+1}
-  V3 rootV;        // velocity written for the root that entered last
+  V3 rootV[2];     // velocity to write for the root(s) in flight: one per 8 slots, two when a chunk holds two strands (N = 4)
   // collision of the vertex waiting for d_{i+1} (its position is final, its velocity is reflected one step later);
   // written by a push-out step, read by the SEP step that follows it
   V3 heldC, heldN;
@@ -200,24 +200,31 @@ __device__ __forceinline__ float max8(const u64 (&v)[4]) {
 
 // One step of the stream pipeline: slot j of the current chunk. Returns whether any lane was pushed out of the
 // collider (warp-uniform), i.e. whether the next step must be the SEP variant.
-//   ROOT : this chunk starts a strand (vertex 0 is in slot 0), so at step j stage j holds a root, and step 7 finalises
-//          the tip of the previous strand.
+//   RS   : root stride of this chunk. 0: no root in it (an inner chunk of a strand); 8: vertex 0 of a strand is in slot 0
+//          (nverts % 8 == 0), so at step j stage j holds a root and step 7 finalises the tip of the previous strand;
+//          4: the chunk holds two whole strands of the reference's own nverts = 4 (interop.h:8), roots in slots 0 and 4.
+//          Stage k holds at step j the vertex of slot j - k (mod 8; negative: of the previous chunk).
 //   SEP  : the previous step had a push-out; inputs come from s.P.
 //   fin_root (runtime, warp-uniform): the vertex finalised by this step is a root.
-template <class PM, bool ORIGIN, bool ROOT, bool SEP>
+template <int RS>
+__device__ __forceinline__ bool root_in_stage(const int j, const int stage) { return RS != 0 && ((j - stage) & (RS - 1)) == 0; }
+
+template <class PM, bool ORIGIN, int RS, bool SEP>
 __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
                                             float4* slotP, float4* slotV, float* slotR) {
   typedef typename PM::S M;
   const float rest_out = *slotR;
-  const V3 rootV_out = s.rootV;
+  const bool set1 = RS == 4 && (j & 4);                                     // which root-velocity set slot j belongs to
+  const V3 rootV_out = set1 ? s.rootV[1] : s.rootV[0];
   V3 x;
   float lx;
   {
     const float4 Pin = *slotP, Vin = *slotV;
     *slotR = Pin.w;
-    if (ROOT && j == 0) {
+    if (root_in_stage<RS>(j, 0)) {
       x = root_transform<M>(V3{ Pin.x, Pin.y, Pin.z });
-      s.rootV = vsub<M>(x, V3{ Pin.x, Pin.y, Pin.z });                      // p.velocity = p.position - lastPosition (cs:192)
+      const V3 rv = vsub<M>(x, V3{ Pin.x, Pin.y, Pin.z });                  // p.velocity = p.position - lastPosition (cs:192)
+      if (set1) s.rootV[1] = rv; else s.rootV[0] = rv;
     } else {
       float4 V = Vin;
       if (a.use_drag) { V.x = M::mul(V.x, a.keep); V.y = M::mul(V.y, a.keep); V.z = M::mul(V.z, a.keep); }
@@ -262,14 +269,16 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #pragma unroll
   for (int q = 3; q >= 0; --q) {
     D[q] = PM::project(s.X[q], vd[q], ninv[q], s.L[q], nz);
-    if (ROOT) {                                                             // the root passes through: D(0, k) = X[0]
+    if (RS == 8) {                                                          // the root passes through: D(0, k) = X[0]
       if (j == q) D[q] = pk3(lo3(in[q]), hi3(D[q]));
       if (j == q + 4) D[q] = pk3(lo3(D[q]), hi3(in[q]));
+    } else if (RS == 4) {                                                   // stages q and q + 4 hold roots at the same steps
+      if (root_in_stage<RS>(j, q)) D[q] = in[q];
     }
     if (q == 3) {
       const V3 dF = vsub<M>(hi3(D[3]), hi3(in[3]));                         // s_particles[i].velocity = p1_bis - p1 (cs:116)
       V3 fw = M::scale(dF, a.damp);                                         // cs:119-121
-      if (ROOT && j == 7) fw = s.heldd;                                     // the tip keeps its own d
+      if (root_in_stage<RS>(j, 7)) fw = s.heldd;                            // the tip (a root follows it) keeps its own d
       s.heldd = dF;
       if (SEP && s.heldHit) fw = M::reflect(fw, s.heldN);                   // cs:137, with the normal found one step ago
       float4 oV = make_float4(fw.x, fw.y, fw.z, 0.f);
@@ -289,12 +298,16 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
     dpc[q] = PM::dot(pt[q], pt[q], nz);
   }
-  if (ROOT) {                                                               // roots do not collide (cs:149-151: index > 0)
+  if (RS == 8) {                                                            // roots do not collide (cs:149-151: index > 0)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (j == q) dpc[q] = pk(__int_as_float(0x7f800000), hi(dpc[q]));
       if (j == q + 4) dpc[q] = pk(lo(dpc[q]), __int_as_float(0x7f800000));
     }
+  } else if (RS == 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (root_in_stage<RS>(j, q)) dpc[q] = pk(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
   }
   const float mnc = min8(dpc);
 
@@ -327,18 +340,21 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 }
 
 // The eight steps of one chunk; `sep` carries the push-out state from step to step.
-template <class PM, bool ORIGIN, bool ROOT>
-__device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pipe& s, bool& sep, const bool prev_root_chunk,
+// `fin_mask`: bit j set when the vertex finalised at step j (slot j of the previous chunk) is a root.
+template <class PM, bool ORIGIN, int RS>
+__device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pipe& s, bool& sep, const unsigned fin_mask,
                                              float4* bP, float4* bV, float* myR, const int sw) {
 #pragma unroll 1
   for (int j = 0; j < kK; ++j) {
-    const bool fin_root = prev_root_chunk && j == 0;
-    if (sep) sep = stream_step<PM, ORIGIN, ROOT, true>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
-    else sep = stream_step<PM, ORIGIN, ROOT, false>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    const bool fin_root = (fin_mask >> j) & 1u;
+    if (sep) sep = stream_step<PM, ORIGIN, RS, true>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    else sep = stream_step<PM, ORIGIN, RS, false>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
   }
 }
 
-template <class PM, bool ORIGIN>
+// NS = 8: a tensor row is one strand of nverts % 8 == 0 vertices. NS = 4: nverts == 4 and a row is TWO consecutive strands
+// (the same 128 bytes), so every chunk is a whole row with roots in slots 0 and 4; a.nstrands is even (launcher).
+template <class PM, bool ORIGIN, int NS>
 #ifndef BH_STREAM_MINB
 #define BH_STREAM_MINB 3
 #endif
@@ -358,8 +374,9 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   const uint32_t tiles_s = base + warp * kWarpTileBytes;
   const uint32_t bar_s = base + kWarps * (kWarpTileBytes + kRingBytes) + warp * 16;
 
-  const int chunks = a.nverts / kK;                                         // per strand
-  const unsigned int ntiles = (unsigned int)((a.nstrands + 31) / 32);
+  const int chunks = NS == 8 ? a.nverts / kK : 1;                           // per row
+  const long long nrows = NS == 8 ? a.nstrands : a.nstrands / 2;
+  const unsigned int ntiles = (unsigned int)((nrows + 31) / 32);
 
   if (lane == 0) {
     mbar_init(bar_s, 1);
@@ -417,7 +434,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       const u64 x = pk(1.0e3f + 10.f * q, 1.0e3f + 10.f * (q + 4)), p = pk(1.0e3f + 10.f * q + 10.f, 1.0e3f + 10.f * (q + 4) + 10.f);
       s.X[q] = { x, x, x }; s.P[q] = { p, p, p }; s.L[q] = 0ull;
     }
-    s.heldd = s.rootV = s.heldC = s.heldN = { 0.f, 0.f, 0.f };
+    s.heldd = s.rootV[0] = s.rootV[1] = s.heldC = s.heldN = { 0.f, 0.f, 0.f };
     s.heldHit = false;
   }
   for (int j = 0; j < kK; ++j) ring[j * 32 + lane] = 0.f;
@@ -433,8 +450,9 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     float4* bP = reinterpret_cast<float4*>(tiles + b * kStageBytes) + lane * 8;
     float4* bV = bP + kPlaneTile / 16;
     const bool root_chunk = !live || cC == 0;
-    if (root_chunk) stream_chunk<PM, ORIGIN, true>(a, nz, s, sep, prev_root_chunk, bP, bV, myR, sw);
-    else stream_chunk<PM, ORIGIN, false>(a, nz, s, sep, prev_root_chunk, bP, bV, myR, sw);
+    if (NS == 4) stream_chunk<PM, ORIGIN, 4>(a, nz, s, sep, 0x11u, bP, bV, myR, sw);
+    else if (root_chunk) stream_chunk<PM, ORIGIN, 8>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
+    else stream_chunk<PM, ORIGIN, 0>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     prev_root_chunk = root_chunk;
     fence_async_smem();                                                     // generic-proxy writes -> visible to the TMA store
     __syncwarp();
@@ -470,9 +488,11 @@ EncodeTiledFn encode_tiled() {
 }
 
 // A plane as a 2-D tensor of fp32: row = strand (stride nverts * 16 B), 4 * nverts floats per row; box = 32 floats x 32 rows.
+// nverts == 4: a row is two consecutive strands (8 vertices, 128 B); nstrands is even.
 bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nverts) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return false;
+  if (nverts == 4) { nstrands /= 2; nverts = 8; }
   const cuuint64_t dims[2] = { (cuuint64_t)nverts * 4, (cuuint64_t)nstrands };
   const cuuint64_t strides[1] = { (cuuint64_t)nverts * 16 };
   const cuuint32_t box[2] = { 32, 32 };
@@ -481,9 +501,9 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct DeviceInfo { int sms = 0; bool ready[4] = { false, false, false, false }; int blocks_per_sm[4] = { 0, 0, 0, 0 }; };
+struct DeviceInfo { int sms = 0; bool ready[8] = {}; int blocks_per_sm[8] = {}; };
 
-template <class PM, bool ORIGIN>
+template <class PM, bool ORIGIN, int NS>
 cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int* tile_counter, int variant) {
   static DeviceInfo info[64];
   static std::mutex mu;
@@ -491,7 +511,7 @@ cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  auto kernel = hair_step_stream_kernel<PM, ORIGIN>;
+  auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS>;
   {
     std::lock_guard<std::mutex> g(mu);
     DeviceInfo& di = info[dev];
@@ -525,7 +545,7 @@ cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int
     }
     mapP = hit->mapP; mapV = hit->mapV;
   }
-  const long long ntiles = (a.nstrands + 31) / 32;
+  const long long ntiles = ((NS == 8 ? a.nstrands : a.nstrands / 2) + 31) / 32;
   long long blocks = (ntiles + kWarps - 1) / kWarps;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
   int per_sm = info[dev].blocks_per_sm[variant];
@@ -570,15 +590,22 @@ cudaError_t selftest_inversesqrt(unsigned long long* mismatches) {
 
 bool stream_kernel_eligible(const StepArgs& a) {
   static const bool disabled = [] { const char* e = getenv("BH_NO_STREAM_KERNEL"); return e && e[0] == '1'; }();
-  return !disabled && a.iterations == kK && a.ncaps == 0 && a.nverts >= kK && a.nverts % kK == 0 &&
+  // nverts % 8 == 0, or the reference's own nverts = 4 (two strands per tensor row: an even number of strands; the
+  // launcher gives the last strand of an odd count to the per-strand kernel)
+  const bool shape_ok = (a.nverts >= kK && a.nverts % kK == 0) || (a.nverts == 4 && a.nstrands >= 2);
+  return !disabled && a.iterations == kK && a.ncaps == 0 && shape_ok &&
          a.nstrands <= 0x7fffffffLL && a.r2 <= 1.8446744073709551616e19f && encode_tiled() != nullptr;
 }
 
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
   // x - (+0.0f) == x bit for bit, for every x (a -0.0f centre component would turn a -0.0f coordinate into +0.0f)
   const bool origin = __builtin_bit_cast(uint32_t, a.cx) == 0u && __builtin_bit_cast(uint32_t, a.cy) == 0u && __builtin_bit_cast(uint32_t, a.cz) == 0u;
-  if (math == 0) return origin ? launch_stream_t<PackedExact, true>(a, stream, tile_counter, 0) : launch_stream_t<PackedExact, false>(a, stream, tile_counter, 1);
-  return origin ? launch_stream_t<PackedFast, true>(a, stream, tile_counter, 2) : launch_stream_t<PackedFast, false>(a, stream, tile_counter, 3);
+  if (a.nverts == 4) {                                                      // a.nstrands is even here (launch_step)
+    if (math == 0) return origin ? launch_stream_t<PackedExact, true, 4>(a, stream, tile_counter, 4) : launch_stream_t<PackedExact, false, 4>(a, stream, tile_counter, 5);
+    return origin ? launch_stream_t<PackedFast, true, 4>(a, stream, tile_counter, 6) : launch_stream_t<PackedFast, false, 4>(a, stream, tile_counter, 7);
+  }
+  if (math == 0) return origin ? launch_stream_t<PackedExact, true, 8>(a, stream, tile_counter, 0) : launch_stream_t<PackedExact, false, 8>(a, stream, tile_counter, 1);
+  return origin ? launch_stream_t<PackedFast, true, 8>(a, stream, tile_counter, 2) : launch_stream_t<PackedFast, false, 8>(a, stream, tile_counter, 3);
 }
 
 }  // namespace bh

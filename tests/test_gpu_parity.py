@@ -329,6 +329,31 @@ def test_stream_kernel_bit_exact(S, N):
     assert_bit_equal(gv, rv, "velocities")
 
 
+@pytest.mark.parametrize("S", [2, 3, 63, 64, 65, 1000, 20001, 131072])
+@pytest.mark.parametrize("sphere", [(0.0, 0.0, 0.0, 1.05), (0.1, -0.05, 0.2, 1.0)])   # reaches past the roots: push-outs from step 1
+def test_stream_kernel_reference_nverts_4_bit_exact(S, sphere):
+    """The reference's own N = 4 (interop.h:8): two strands per 128-byte tensor row, roots in slots 0 and 4 of every
+    chunk; an odd strand count leaves the last strand to the per-strand kernel."""
+    N = 4
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(12):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.45, sphere=sphere)
+        assert sim.kernel_kind == 0
+        sim.upload(pos, vel)
+        for _ in range(12):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+    touching = np.linalg.norm(rp[:, :3] - np.float32(sphere[:3]), axis=1) < sphere[3] * (1 + 1e-6)
+    if S >= 1000:
+        assert touching.reshape(S, N)[:, 1:].any(), "the case must exercise the push-out"
+
+
 def test_stream_kernel_off_origin_sphere_bit_exact():
     S, N = 3000, 32
     sphere = (0.1, -0.05, 0.2, 0.9)

@@ -117,7 +117,7 @@ def test_hair_setup_from_obj_reference_default_shape_bit_exact(tmp_path):
     h.set_bounding_sphere(sphere)
     h.setup(path)
     assert h.initialized() and h.nroots == S == n * n
-    assert h.sim.kernel_kind == 1                      # N = 4: the per-strand pipelined kernel
+    assert h.sim.kernel_kind == 0                      # N = 4: the streaming kernel, two strands per 128-byte tensor row
     for _ in range(10):
         h.update(float(DT))
     gp, gv, gt = h.sim.download(tan=True)
