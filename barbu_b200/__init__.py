@@ -6,7 +6,8 @@ include/barbu_hair.h), the build recipe, and the host-side mirror of the referen
 from .hair import (BH_MATH_EXACT, BH_MATH_FAST, BarbuHairError, BhParams, BhStateInfo, Hair, HairSim, PinnedBuffer, ScalpMesh,
                    build_patch_indices, default_params, init_tangents_host, load_library, load_obj_scalp, peek_state, random_values,
                    selftest_math, sphere_scalp_triangles)
+from .marschner import BhMarschnerParams, Marschner, generate_luts
 
-__all__ = ["BH_MATH_EXACT", "BH_MATH_FAST", "BarbuHairError", "BhParams", "BhStateInfo", "Hair", "HairSim", "PinnedBuffer",
+__all__ = ["BhMarschnerParams", "Marschner", "generate_luts", "BH_MATH_EXACT", "BH_MATH_FAST", "BarbuHairError", "BhParams", "BhStateInfo", "Hair", "HairSim", "PinnedBuffer",
            "ScalpMesh", "build_patch_indices", "default_params", "init_tangents_host", "load_library", "load_obj_scalp", "peek_state",
            "random_values", "selftest_math", "sphere_scalp_triangles"]

@@ -32,6 +32,7 @@ ABI_SYMBOLS = (
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
+    "bh_marschner_default_params", "bh_marschner_generate",
 )
 
 

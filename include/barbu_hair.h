@@ -184,6 +184,22 @@ int  bh_peek_state(const char* path, bh_state_info* info);
  * (BH_ERR_INVALID on mismatch: the sim then holds no valid state) and adopts the stored parameters. */
 int  bh_load_state(bh_sim* sim, const char* path, bh_state_info* info /* may be NULL */);
 
+/* ---- next stage: the Marschner lookup tables of the render path ------------------------------------- */
+/* Marschner::generate (src/fx/marschner.cc:35-69): cs_marschner_m.glsl + cs_marschner_n.glsl over a resolution^2 image
+ * (kTextureResolution = 128, marschner.h:28), GL_RGBA16F texels, texel (x, y) at index y * resolution + x.
+ *   M: (M_R, M_TT, M_TRT, cos theta_d) at (sin theta_i, sin theta_r) = 2 (x, y) / resolution - 1
+ *   N: (N_R, N_TT, N_TRT, 1)          at (cos phi_d,  cos theta_d)  = 2 (x, y) / resolution - 1
+ * Field defaults: Marschner::ShadingParameters_t (marschner.h:38-52). Any output pointer may be NULL; the rgba32f
+ * outputs are the texels before the half-float store. Transcendental functions are CUDA's: a few ulp from a GL driver's. */
+typedef struct bh_marschner_params {
+  float eta, absorption, eccentricity;                 /* fiber properties  -> uEta, uAbsorption, uEccentricity */
+  float ar, br;                                        /* surface           -> uLongitudinalShift, uLongitudinalWidth */
+  float glint_scale, azimuthal_width, delta_caustic, delta_hm;   /* glints (unused by the shaders' active branch) */
+} bh_marschner_params;
+void bh_marschner_default_params(bh_marschner_params* p);
+int  bh_marschner_generate(const bh_marschner_params* p, int resolution, int device, uint16_t* m_rgba16f,
+                           uint16_t* n_rgba16f, float* m_rgba32f, float* n_rgba32f);
+
 /* ---- CUDA-GL interop on buffer 0 (pbuffer_.read_ssbo_id(), hair.cc:371) --------------------- */
 /* cudaGraphicsGLRegisterBuffer; while registered, bh_step maps the GL buffer, steps in place and
  * unmaps, so the render VAO (hair.cc:371-389) sees the new positions without a copy. Needs a

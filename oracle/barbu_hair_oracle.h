@@ -97,6 +97,10 @@ int64_t bho_tess_stream_count(int64_t npatches, int ninstances, int nlines, int 
 void bho_tess_stream(const float* pos4, const float* tan4, const int32_t* patch_indices, int64_t npatches, int nverts,
                      float scale, int ninstances, int nlines, int nsubsegments, uint32_t seed, float* out4);
 
+/* Marschner lookup tables (barbu_marschner_oracle.c; cs_marschner_m.glsl / cs_marschner_n.glsl): fp32 RGBA texels. */
+void bho_marschner_luts(const float* params9, int resolution, float* m_rgba, float* n_rgba);
+void bho_float_to_half(const float* in, int64_t count, uint16_t* out);     /* GL_RGBA16F store, round to nearest even */
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,13 @@ What it produces
       (1) HAIR_MAX_PARTICLE_PER_STRAND is re-#defined to REF_N after interop.h;
       (2) `memoryBarrierShared()` is a real workgroup barrier (fiber yield) — the evident intent,
           and what a <=32-wide workgroup computes on lock-step hardware.
+  _ref/marschner.gen.inc       the Marschner LUT shaders: shared/inc_constants.glsl, the two
+                               `gaussian` overloads of shared/inc_maths.glsl:270-276, shared/inc_fresnel.glsl,
+                               shared/inc_solver.glsl, hair/marschner/inc_marschner_n.glsl and the `main` of
+                               cs_marschner_m.glsl / cs_marschner_n.glsl (-> marschner_m_main / marschner_n_main), with
+                               the same lexical edits plus: `#include`/include guards, `precision`, `layout(...) in;`
+                               and the image declaration removed (the harness provides imageStore), and the one
+                               swizzle assignment `roots.xyz = e;` spelled component-wise.
   _ref/hair_init_simulation.gen.inc   body of Hair::init_simulation, src/fx/hair.cc:236-328
                                       (up to, not including, the GL buffer creation).
   _ref/hair_init_mesh.gen.inc         element loop of Hair::init_mesh, src/fx/hair.cc:397-409.
@@ -53,6 +60,46 @@ def gen_shader():
     open(os.path.join(OUT, "cs_simulation.gen.inc"), "w").write(src)
 
 
+FLOAT_LITERAL = r"(?<![\w.])(\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?)(?![\w.])"
+
+
+def glsl_to_cpp(src):
+    """The lexical edits shared by the Marschner sources (see the module docstring)."""
+    src = re.sub(r"^#version.*$", "", src, flags=re.M)
+    src = re.sub(r'^#include\s+".*$', "", src, flags=re.M)
+    src = re.sub(r"^#(ifndef|define|endif)\s*(//\s*)?SHADERS?_\w*GLSL_\s*$", "", src, flags=re.M)
+    src = re.sub(r"^precision\s+highp\s+float;\s*$", "", src, flags=re.M)
+    src = re.sub(r"^layout\(local_size_x[^)]*\)\s*in;\s*$", "", src, flags=re.M)
+    src = re.sub(r"^\s*writeonly\s*(\n\s*)?uniform\s+layout\(rgba16f\)\s+image2D\s+uDstImg;\s*$", "", src, flags=re.M)
+    src = re.sub(r"\bin\s+(vec[234]|float|int)\b", r"\1", src)
+    src = re.sub(r"(\w+)\.xyz\s*=\s*([^;]*);", r"{ const vec3 t_ = \2; \1.x = t_.x; \1.y = t_.y; \1.z = t_.z; }", src)
+    src = re.sub(r"\.xyz\b(?!\()", ".xyz()", src)
+    src = re.sub(r"\.xy\b(?!\()", ".xy()", src)
+    return re.sub(FLOAT_LITERAL, r"\1f", src)
+
+
+def gen_marschner():
+    sh = os.path.join(REF, "src/shaders")
+    parts = []
+    parts.append(glsl_to_cpp(open(os.path.join(sh, "shared/inc_constants.glsl")).read()))
+    maths = open(os.path.join(sh, "shared/inc_maths.glsl")).read()
+    g = re.findall(r"^(?:float|vec3) gaussian\([^)]*\) \{\n.*?\n\}\n", maths, flags=re.M | re.S)
+    assert len(g) == 2, f"expected two gaussian overloads in inc_maths.glsl, found {len(g)}"
+    parts.append(glsl_to_cpp("".join(g)))
+    for f in ("shared/inc_fresnel.glsl", "shared/inc_solver.glsl", "hair/marschner/inc_marschner_n.glsl"):
+        parts.append(glsl_to_cpp(open(os.path.join(sh, f)).read()))
+    for f, name in (("hair/marschner/cs_marschner_m.glsl", "marschner_m_main"), ("hair/marschner/cs_marschner_n.glsl", "marschner_n_main")):
+        src = glsl_to_cpp(open(os.path.join(sh, f)).read())
+        src, n = re.subn(r"\bvoid\s+main\s*\(\s*\)", f"void {name}()", src); assert n == 1
+        src = re.sub(r"^#ifndef BLOCK_DIM\s*\n\s*#define BLOCK_DIM\s+16\s*\n#endif\s*$", "", src, flags=re.M)
+        if name == "marschner_n_main":                     # both programs declare it; one C++ translation unit holds both
+            src, n = re.subn(r"^uniform float uInvResolution;\s*$", "", src, flags=re.M); assert n == 1
+        parts.append(src)
+    out = "\n".join(parts)
+    assert "imageStore" in out and "uDstImg;" not in out and "#include" not in out
+    open(os.path.join(OUT, "marschner.gen.inc"), "w").write(out)
+
+
 def slice_lines(path, first, last):
     lines = open(os.path.join(REF, path)).read().split("\n")
     return "\n".join(lines[first - 1:last]) + "\n"
@@ -74,4 +121,5 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_shader()
     gen_host()
+    gen_marschner()
     print("generated into", OUT)

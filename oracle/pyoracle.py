@@ -29,8 +29,8 @@ class BhoParams(C.Structure):
 
 
 def build_oracle(force: bool = False) -> str:
-    src = os.path.join(HERE, "barbu_hair_oracle.c")
-    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("barbu_hair_oracle.c", "barbu_marschner_oracle.c", "barbu_hair_oracle.h")]
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
     return ORACLE_SO
 
@@ -238,3 +238,39 @@ def obj_scalp(path: str):
     P = np.array([pos[k[0]] for k in uniq], np.float32).reshape(-1, 3)
     Nn = np.array([nrm[k[2]] for k in uniq], np.float32).reshape(-1, 3)
     return P, Nn, np.array(idx, np.int32).reshape(-1, 3)
+
+
+# ---- Marschner lookup tables -------------------------------------------------------------------
+MARSCHNER_DEFAULTS = dict(eta=1.55, absorption=0.20, eccentricity=0.85, ar=-5.0, br=5.0, glintScale=0.5, azimuthalWidth=10.0,
+                          deltaCaustic=0.2, deltaHm=0.5)                       # marschner.h:38-52
+
+
+def marschner_params(**kw) -> np.ndarray:
+    d = dict(MARSCHNER_DEFAULTS); d.update(kw)
+    return np.array([d[k] for k in MARSCHNER_DEFAULTS], np.float32)
+
+
+def marschner_luts(params, resolution: int = 128):
+    """(M, N) lookup tables as (res, res, 4) float32, texel (x, y) at [y, x]."""
+    m = np.empty((resolution, resolution, 4), np.float32); n = np.empty_like(m)
+    oracle().bho_marschner_luts(_p(np.ascontiguousarray(params, np.float32)), C.c_int(resolution), _p(m), _p(n))
+    return m, n
+
+
+def float_to_half(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.empty(a.shape, np.uint16)
+    oracle().bho_float_to_half(_p(a), C.c_int64(a.size), _p(out))
+    return out
+
+
+def ref_marschner_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libbarbu_ref_marschner.so"))
+
+
+def ref_marschner_luts(params, resolution: int = 128):
+    """The reference shader SOURCES run on the CPU (oracle/_ref/libbarbu_ref_marschner.so)."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libbarbu_ref_marschner.so"))
+    m = np.empty((resolution, resolution, 4), np.float32); n = np.empty_like(m)
+    lib.ref_marschner_luts(_p(np.ascontiguousarray(params, np.float32)), C.c_int(resolution), _p(m), _p(n))
+    return m, n
