@@ -23,6 +23,7 @@
 // Algorithmic traffic: 16 B pos + 16 B vel read, the same written = 64 B per vertex per launch.
 #include "hair_step.cuh"
 #include "hair_math.cuh"
+#include "hair_collide.cuh"
 
 #include <cstdlib>
 
@@ -36,66 +37,6 @@ constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 // per warp: position slots, velocity slots (32 * kPitch float4 each) + rest-length ring (8 * 32 floats)
 constexpr int kWarpSmemBytes = 2 * 32 * kPitch * 16 + kChunk * 32 * 4;
-
-// Closest point on the capsule axis, then the same push-out as the sphere. Extension (no reference).
-template <class M>
-__device__ __forceinline__ V3 capsule_center(const Capsule& c, V3 p) {
-  V3 a = { c.ax, c.ay, c.az };
-  const V3 ab = { M::sub(c.bx, c.ax), M::sub(c.by, c.ay), M::sub(c.bz, c.az) };
-  const float l2 = M::dot(ab, ab);
-  if (l2 > 0.0f) {
-    const V3 ap = vsub<M>(p, a);
-    float t = __fdiv_rn(M::dot(ap, ab), l2);
-    t = fminf(fmaxf(t, 0.0f), 1.0f);
-    a = { M::add(c.ax, M::mul(t, ab.x)), M::add(c.ay, M::mul(t, ab.y)), M::add(c.az, M::mul(t, ab.z)) };
-  }
-  return a;
-}
-
-// CollideSphere(+1, c, r, p) on the position only (iterations whose velocity is dead).
-template <class M>
-__device__ __forceinline__ V3 collide_pos(V3 p, V3 c, float r, float r2) {
-  const V3 pt = vsub<M>(p, c);
-  const float dp = M::dot(pt, pt);
-  if (dp < r2) {
-    const V3 n = M::scale(pt, M::inversesqrt(dp));
-    p = M::push_out(c, n, r);
-  }
-  return p;
-}
-// ... and on position + velocity (last iteration): vel = reflect(vel, n).
-template <class M>
-__device__ __forceinline__ void collide_pos_vel(V3& p, V3& w, V3 c, float r, float r2) {
-  const V3 pt = vsub<M>(p, c);
-  const float dp = M::dot(pt, pt);
-  if (dp < r2) {
-    const V3 n = M::scale(pt, M::inversesqrt(dp));
-    p = M::push_out(c, n, r);
-    w = M::reflect(w, n);
-  }
-}
-
-template <class M, bool CAPS>
-__device__ __forceinline__ V3 collide_all_pos(const StepArgs& a, V3 p) {
-  p = collide_pos<M>(p, V3{ a.cx, a.cy, a.cz }, a.r, a.r2);
-  if (CAPS) {
-    for (int q = 0; q < a.ncaps; ++q) {
-      const float r = a.caps[q].r;
-      p = collide_pos<M>(p, capsule_center<M>(a.caps[q], p), r, M::mul(r, r));
-    }
-  }
-  return p;
-}
-template <class M, bool CAPS>
-__device__ __forceinline__ void collide_all_pos_vel(const StepArgs& a, V3& p, V3& w) {
-  collide_pos_vel<M>(p, w, V3{ a.cx, a.cy, a.cz }, a.r, a.r2);
-  if (CAPS) {
-    for (int q = 0; q < a.ncaps; ++q) {
-      const float r = a.caps[q].r;
-      collide_pos_vel<M>(p, w, capsule_center<M>(a.caps[q], p), r, M::mul(r, r));
-    }
-  }
-}
 
 // One FTL projection: D = p0 + L * normalize(prev - p0).
 template <class M>

@@ -25,6 +25,9 @@ struct StepArgs {
   int use_drag;
   int ncaps;
   Capsule caps[kMaxCapsules];
+  // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
+  // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.
+  float capb[kMaxCapsules][4];
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.

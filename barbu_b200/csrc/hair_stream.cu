@@ -25,10 +25,12 @@
 // Algorithmic traffic: 16 B pos + 16 B vel read and the same written = 64 B per vertex per launch.
 #include "hair_step.cuh"
 #include "hair_math.cuh"
+#include "hair_collide.cuh"
 
 #include <cuda.h>
 
 #include <cstdint>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -86,7 +88,9 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 mul2_contractable(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }
+// written as two float negations so that ptxas folds it into the consumer's operand modifier (FFMA2 -R); an integer xor
+// of the sign bits costs two LOP3 per use
+__device__ __forceinline__ u64 neg2(u64 a) { return pk(-lo(a), -hi(a)); }
 __device__ __forceinline__ float rsq_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -175,6 +179,7 @@ struct Pipe {
   // written by a push-out step, read by the SEP step that follows it
   V3 heldC, heldN;
   bool heldHit;
+  bool heldCap;    // capsule variant, warp-uniform: that vertex went through the capsule chain -> recompute it with its velocity
 };
 
 template <class PM> __device__ __noinline__ u64 neg_inversesqrt_slow(u64 x) { return PM::neg_inversesqrt_ieee(x); }
@@ -207,9 +212,51 @@ __device__ __forceinline__ float max8(const u64 (&v)[4]) {
 //   SEP  : the previous step had a push-out; inputs come from s.P.
 //   fin_root (runtime, warp-uniform): the vertex finalised by this step is a root.
 template <int RS>
-__device__ __forceinline__ bool root_in_stage(const int j, const int stage) { return RS != 0 && ((j - stage) & (RS - 1)) == 0; }
+__device__ __forceinline__ bool root_in_stage(const int j, const int stage) {
+  return RS == 8 ? j == stage : (RS != 0 && ((j - stage) & (RS - 1)) == 0);  // j, stage in 0..7; j >= 8 (RS == 8): no root in this chunk
+}
 
-template <class PM, bool ORIGIN, int RS, bool SEP>
+//   CAPS : capsule colliders are present (extension, a.ncaps > 0). Every step tests the eight new positions against the
+//          capsules' bounding spheres (packed, conservative); only a warp that may touch one runs the exact capsule
+//          arithmetic (scalar, hair_collide.cuh). The vertex leaving the pipeline then recomputes its whole collision
+//          chain with its final velocity one step later, so no collision normals are carried.
+// The exact capsule arithmetic runs for few warps and must not bloat the step body (the instruction cache holds the hot
+// loop only if the rare paths stay out of line): one out-of-line copy each, called per vertex.
+struct Pos8 { V3p c[4]; };                       // the eight positions of a step: pair q = stages q (lo) and q + 4 (hi)
+template <class M> __device__ __noinline__ Pos8 caps_slow(const StepArgs& a, Pos8 x, const unsigned skip) {
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    V3 l = lo3(x.c[q]), h = hi3(x.c[q]);
+    if (!((skip >> q) & 1u)) l = collide_caps_pos_bounded<M>(a, l);
+    if (!((skip >> (q + 4)) & 1u)) h = collide_caps_pos_bounded<M>(a, h);
+    x.c[q] = pk3(l, h);
+  }
+  return x;
+}
+struct PosVel { V3 p, w; };
+template <class M> __device__ __noinline__ PosVel all_pos_vel_slow(const StepArgs& a, V3 p, V3 w) {
+  collide_all_pos_vel_bounded<M>(a, p, w);
+  return { p, w };
+}
+
+// Conservative capsule test of eight positions: true when some position lies inside a capsule's bounding sphere.
+__device__ __forceinline__ bool caps_may_touch(const StepArgs& a, const V3p (&X)[4]) {
+  bool touch = false;
+#pragma unroll 1
+  for (int k = 0; k < a.ncaps; ++k) {
+    const V3p m = { pk(a.capb[k][0], a.capb[k][0]), pk(a.capb[k][1], a.capb[k][1]), pk(a.capb[k][2], a.capb[k][2]) };
+    u64 dd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const V3p e = sub3(X[q], m);
+      dd[q] = fma2(e.z, e.z, fma2(e.y, e.y, mul2_contractable(e.x, e.x)));  // a bound, not a result: contraction is fine
+    }
+    touch = touch || (min8(dd) < a.capb[k][3]);
+  }
+  return touch;
+}
+
+template <class PM, bool ORIGIN, int RS, bool SEP, bool CAPS>
 __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
                                             float4* slotP, float4* slotV, float* slotR) {
   typedef typename PM::S M;
@@ -236,8 +283,8 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   // ---- the vertex finalised by this step (t-8): position known since the previous step ------------
   const V3 fin = hi3(s.X[3]);                                               // D(i, 8)
   V3 fp = fin;
-  if (SEP) { fp.x = s.heldHit ? s.heldC.x : fin.x; fp.y = s.heldHit ? s.heldC.y : fin.y; fp.z = s.heldHit ? s.heldC.z : fin.z; }
-  float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out);
+  const bool recompute = SEP && CAPS && s.heldCap;
+  if (SEP && !recompute) { fp.x = s.heldHit ? s.heldC.x : fin.x; fp.y = s.heldHit ? s.heldC.y : fin.y; fp.z = s.heldHit ? s.heldC.z : fin.z; }
 
   // inputs of the eight stages: stage 0 takes the new vertex, stage k > 0 what stage k-1 produced in the previous step
   V3p in[4];
@@ -280,7 +327,11 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
       V3 fw = M::scale(dF, a.damp);                                         // cs:119-121
       if (root_in_stage<RS>(j, 7)) fw = s.heldd;                            // the tip (a root follows it) keeps its own d
       s.heldd = dF;
-      if (SEP && s.heldHit) fw = M::reflect(fw, s.heldN);                   // cs:137, with the normal found one step ago
+      if (SEP && !recompute && s.heldHit) fw = M::reflect(fw, s.heldN);     // cs:137, with the normal found one step ago
+      if (recompute) {                                                      // sphere + capsules again from D(i, 8), now with the velocity
+        const PosVel pv = all_pos_vel_slow<M>(a, fp, fw); fp = pv.p; fw = pv.w;
+      }
+      const float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out);
       float4 oV = make_float4(fw.x, fw.y, fw.z, 0.f);
       if (fin_root) oV = make_float4(rootV_out.x, rootV_out.y, rootV_out.z, 0.f);   // a root is neither moved nor reflected
       *slotP = oP;
@@ -313,12 +364,12 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 
   // ---- phase B: push-outs, only when some lane of the warp touches the sphere --------------------
   const bool any_hit = __any_sync(0xffffffffu, mnc < a.r2);
-  if (any_hit) {
+  V3p C[4];
+  auto sphere_push_out = [&]() {
     // a hit has dpc < r2 < inf (launcher guarantees), so only the lower bound of the branch-free range can fail
     u64 ninvc[4];
     neg_inversesqrt_batch<PM>(dpc, ninvc, !(mnc < M::kFastLo), nz);
     const u64 r2p = pk(a.r, a.r);
-    V3p C[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const V3p Q = PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
@@ -331,30 +382,53 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     s.heldHit = hi(dpc[3]) < a.r2;
     s.heldC = hi3(C[3]);
     s.heldN = M::scale(hi3(pt[3]), PM::inv_of(hi(ninvc[3])));
-    // the moved vertices enter the next step through P: stage k+1 takes C of stage k
+  };
+  auto enter_through_P = [&]() {                                            // stage k+1 takes C of stage k
 #pragma unroll
     for (int q = 3; q >= 1; --q) s.P[q] = C[q - 1];
     s.P[0] = pk3(V3{ 0.f, 0.f, 0.f }, lo3(C[3]));
+  };
+  if (!CAPS) {
+    if (any_hit) { sphere_push_out(); enter_through_P(); }
+    return any_hit;
   }
-  return any_hit;
+  // ---- capsule extension: bound test on the positions as the sphere left them, exact chain out of line ------------
+#pragma unroll
+  for (int q = 0; q < 4; ++q) C[q] = D[q];
+  if (any_hit) sphere_push_out(); else s.heldHit = false;
+  const bool any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
+  if (any_cap) {
+    // every vertex in flight that is not a root (cs:149-151: index > 0); the vertex in stage 7 is skipped, the next step
+    // recomputes its whole chain (sphere included) together with its velocity
+    unsigned skip = 0x80u;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) skip |= root_in_stage<RS>(j, k) ? (1u << k) : 0u;
+    const Pos8 r = caps_slow<M>(a, Pos8{ { C[0], C[1], C[2], C[3] } }, skip);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) C[q] = r.c[q];
+  }
+  s.heldCap = any_cap && !root_in_stage<RS>(j, 7);                          // conservative: recomputing without a hit is a no-op
+  if (any_hit || any_cap) enter_through_P();
+  return any_hit || any_cap;
 }
 
 // The eight steps of one chunk; `sep` carries the push-out state from step to step.
 // `fin_mask`: bit j set when the vertex finalised at step j (slot j of the previous chunk) is a root.
-template <class PM, bool ORIGIN, int RS>
+template <class PM, bool ORIGIN, int RS, bool CAPS>
 __device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pipe& s, bool& sep, const unsigned fin_mask,
-                                             float4* bP, float4* bV, float* myR, const int sw) {
+                                             float4* bP, float4* bV, float* myR, const int sw, const int joff = 0) {
+  // joff = 8 (RS == 8 only): the chunk holds no root; the step sees slot numbers 8..15, which match no stage
 #pragma unroll 1
   for (int j = 0; j < kK; ++j) {
     const bool fin_root = (fin_mask >> j) & 1u;
-    if (sep) sep = stream_step<PM, ORIGIN, RS, true>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
-    else sep = stream_step<PM, ORIGIN, RS, false>(a, nz, s, j, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    if (sep) sep = stream_step<PM, ORIGIN, RS, true, CAPS>(a, nz, s, j + joff, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    else sep = stream_step<PM, ORIGIN, RS, false, CAPS>(a, nz, s, j + joff, fin_root, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
   }
 }
 
 // NS = 8: a tensor row is one strand of nverts % 8 == 0 vertices. NS = 4: nverts == 4 and a row is TWO consecutive strands
 // (the same 128 bytes), so every chunk is a whole row with roots in slots 0 and 4; a.nstrands is even (launcher).
-template <class PM, bool ORIGIN, int NS>
+template <class PM, bool ORIGIN, int NS, bool CAPS>
 #ifndef BH_STREAM_MINB
 #define BH_STREAM_MINB 3
 #endif
@@ -435,7 +509,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       s.X[q] = { x, x, x }; s.P[q] = { p, p, p }; s.L[q] = 0ull;
     }
     s.heldd = s.rootV[0] = s.rootV[1] = s.heldC = s.heldN = { 0.f, 0.f, 0.f };
-    s.heldHit = false;
+    s.heldHit = s.heldCap = false;
   }
   for (int j = 0; j < kK; ++j) ring[j * 32 + lane] = 0.f;
 
@@ -450,9 +524,11 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     float4* bP = reinterpret_cast<float4*>(tiles + b * kStageBytes) + lane * 8;
     float4* bV = bP + kPlaneTile / 16;
     const bool root_chunk = !live || cC == 0;
-    if (NS == 4) stream_chunk<PM, ORIGIN, 4>(a, nz, s, sep, 0x11u, bP, bV, myR, sw);
-    else if (root_chunk) stream_chunk<PM, ORIGIN, 8>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
-    else stream_chunk<PM, ORIGIN, 0>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
+    if (NS == 4) stream_chunk<PM, ORIGIN, 4, CAPS>(a, nz, s, sep, 0x11u, bP, bV, myR, sw);
+    // capsule variant: one step body for both kinds of chunk (its extra tests already crowd the instruction cache)
+    else if (CAPS) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw, root_chunk ? 0 : 8);
+    else if (root_chunk) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
+    else stream_chunk<PM, ORIGIN, 0, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     prev_root_chunk = root_chunk;
     fence_async_smem();                                                     // generic-proxy writes -> visible to the TMA store
     __syncwarp();
@@ -501,17 +577,33 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct DeviceInfo { int sms = 0; bool ready[8] = {}; int blocks_per_sm[8] = {}; };
+struct DeviceInfo { int sms = 0; bool ready[12] = {}; int blocks_per_sm[12] = {}; };
 
-template <class PM, bool ORIGIN, int NS>
-cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int* tile_counter, int variant) {
+// Bounding sphere of capsule k for caps_may_touch(): centre = midpoint of the axis, radius = half axis + capsule radius,
+// widened by 1e-3 relative + 1e-6 absolute — orders of magnitude above the fp32 rounding of either the bound or the exact
+// test it guards, so "outside the bound" implies "the exact test cannot fire".
+void fill_capsule_bounds(StepArgs& b) {
+  for (int k = 0; k < b.ncaps && k < kMaxCapsules; ++k) {
+    const Capsule& c = b.caps[k];
+    const double hx = 0.5 * ((double)c.bx - c.ax), hy = 0.5 * ((double)c.by - c.ay), hz = 0.5 * ((double)c.bz - c.az);
+    const double R = (std::sqrt(hx * hx + hy * hy + hz * hz) + std::fabs((double)c.r)) * (1.0 + 1e-3) + 1e-6;
+    b.capb[k][0] = (float)(c.ax + hx); b.capb[k][1] = (float)(c.ay + hy); b.capb[k][2] = (float)(c.az + hz);
+    b.capb[k][3] = std::nextafter((float)(R * R), INFINITY);
+    if (!(b.capb[k][3] == b.capb[k][3])) b.capb[k][3] = INFINITY;            // NaN capsule: always take the exact path
+  }
+}
+
+template <class PM, bool ORIGIN, int NS, bool CAPS = false>
+cudaError_t launch_stream_t(const StepArgs& a_in, cudaStream_t stream, unsigned int* tile_counter, int variant) {
+  StepArgs a = a_in;
+  if (CAPS) fill_capsule_bounds(a);
   static DeviceInfo info[64];
   static std::mutex mu;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS>;
+  auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS, CAPS>;
   {
     std::lock_guard<std::mutex> g(mu);
     DeviceInfo& di = info[dev];
@@ -593,13 +685,17 @@ bool stream_kernel_eligible(const StepArgs& a) {
   // nverts % 8 == 0, or the reference's own nverts = 4 (two strands per tensor row: an even number of strands; the
   // launcher gives the last strand of an odd count to the per-strand kernel)
   const bool shape_ok = (a.nverts >= kK && a.nverts % kK == 0) || (a.nverts == 4 && a.nstrands >= 2);
-  return !disabled && a.iterations == kK && a.ncaps == 0 && shape_ok &&
+  return !disabled && a.iterations == kK && a.ncaps >= 0 && a.ncaps <= kMaxCapsules && shape_ok &&
          a.nstrands <= 0x7fffffffLL && a.r2 <= 1.8446744073709551616e19f && encode_tiled() != nullptr;
 }
 
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
   // x - (+0.0f) == x bit for bit, for every x (a -0.0f centre component would turn a -0.0f coordinate into +0.0f)
   const bool origin = __builtin_bit_cast(uint32_t, a.cx) == 0u && __builtin_bit_cast(uint32_t, a.cy) == 0u && __builtin_bit_cast(uint32_t, a.cz) == 0u;
+  if (a.ncaps > 0) {                                                        // capsule extension: one variant per profile and row shape
+    if (a.nverts == 4) return math == 0 ? launch_stream_t<PackedExact, false, 4, true>(a, stream, tile_counter, 8) : launch_stream_t<PackedFast, false, 4, true>(a, stream, tile_counter, 9);
+    return math == 0 ? launch_stream_t<PackedExact, false, 8, true>(a, stream, tile_counter, 10) : launch_stream_t<PackedFast, false, 8, true>(a, stream, tile_counter, 11);
+  }
   if (a.nverts == 4) {                                                      // a.nstrands is even here (launch_step)
     if (math == 0) return origin ? launch_stream_t<PackedExact, true, 4>(a, stream, tile_counter, 4) : launch_stream_t<PackedExact, false, 4>(a, stream, tile_counter, 5);
     return origin ? launch_stream_t<PackedFast, true, 4>(a, stream, tile_counter, 6) : launch_stream_t<PackedFast, false, 4>(a, stream, tile_counter, 7);

@@ -382,6 +382,88 @@ def test_stream_and_per_strand_kernels_agree(monkeypatch):
     assert_bit_equal(gv, rv, "velocities")
 
 
+def _capsule_params(caps, **kw):
+    """(oracle params, device params) carrying the same capsules."""
+    par = po.default_params(ncapsules=len(caps), **kw)
+    gcfg = bb.default_params()
+    gcfg.scale, gcfg.ncapsules = kw["scale"], len(caps)
+    for i, x in enumerate(kw["sphere"]):
+        gcfg.sphere[i] = x
+    for q, (a, b, r) in enumerate(caps):
+        for i in range(3):
+            par.capsules[q].a[i], par.capsules[q].b[i] = a[i], b[i]
+            gcfg.capsules[q].a[i], gcfg.capsules[q].b[i] = a[i], b[i]
+        par.capsules[q].radius = gcfg.capsules[q].radius = r
+    return par, gcfg
+
+
+CAPSULE_SETS = {
+    # two "arms" leaving the scalp: roots inside the capsules, long contact along the axis
+    "arms": [((0.55, 0.25, 0.0), (1.25, -0.35, 0.0), 0.30), ((-0.55, 0.25, 0.0), (-1.25, -0.35, 0.0), 0.30)],
+    # overlapping capsules + a degenerate one (a == b: a sphere) + one far away that is never touched
+    "overlap": [((0.0, 1.0, 0.0), (0.3, 1.4, 0.2), 0.25), ((0.1, 1.1, 0.1), (0.1, 1.1, 0.1), 0.3),
+                ((0.2, 1.2, 0.0), (-0.4, 1.3, 0.1), 0.2), ((50.0, 0.0, 0.0), (51.0, 0.0, 0.0), 0.5)],
+    # eight capsules (the maximum) in a ring below the scalp, where the strands hang
+    "ring8": [((float(np.cos(k * np.pi / 4)), -1.1, float(np.sin(k * np.pi / 4))),
+               (float(np.cos((k + 1) * np.pi / 4)), -1.25, float(np.sin((k + 1) * np.pi / 4))), 0.12) for k in range(8)],
+}
+
+
+@pytest.mark.parametrize("caps", sorted(CAPSULE_SETS))
+@pytest.mark.parametrize("S,N,sphere", [(600, 16, SPHERE), (4100, 32, SPHERE), (1001, 8, (0.05, 0.1, -0.02, 0.9)),
+                                        (2050, 4, (0.0, 0.0, 0.0, 1.02)), (333, 64, SPHERE)])
+def test_stream_kernel_capsules_bit_exact(caps, S, N, sphere):
+    """Capsule colliders (extension, oracle-defined) through the streaming kernel: conservative bounding test, exact
+    capsule chain for the warps that may touch, collision chain of the leaving vertex recomputed with its velocity."""
+    capsules = CAPSULE_SETS[caps]
+    pos, vel = ragged_state(S, N)
+    par, gcfg = _capsule_params(capsules, dt=float(DT), scale=1.45, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    nsteps = 14
+    for _ in range(nsteps):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        assert sim.kernel_kind == 0, "capsules must not leave the streaming kernel"
+        sim.upload(pos, vel)
+        for _ in range(nsteps):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+    if caps != "ring8" or N >= 16:
+        # the case must exercise the capsule push-out: some non-root vertex sits on a capsule surface
+        x = rp[:, :3].astype(np.float64).reshape(S, N, 3)[:, 1:].reshape(-1, 3)
+        on = np.zeros(len(x), bool)
+        for a, b, r in capsules:
+            a, b = np.array(a), np.array(b)
+            ab = b - a
+            t = np.clip((x - a) @ ab / max(ab @ ab, 1e-30), 0, 1) if ab @ ab > 0 else np.zeros(len(x))
+            d = np.linalg.norm(x - (a + t[:, None] * ab), axis=1)
+            on |= np.abs(d - r) < 1e-5
+        assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
+
+
+def test_stream_kernel_capsules_fast_profile_close_to_exact():
+    """Fast profile with capsules: same contacts, positions within the one-step tolerance of the exact profile."""
+    S, N = 2048, 32
+    pos, vel = ragged_state(S, N)
+    par, gcfg = _capsule_params(CAPSULE_SETS["arms"], dt=float(DT), scale=1.45, sphere=SPHERE)
+    out = {}
+    for math in (bb.BH_MATH_EXACT, bb.BH_MATH_FAST):
+        gcfg.math = math
+        with bb.HairSim(S, N) as sim:
+            sim.set_params(gcfg)
+            sim.upload(pos, vel)
+            for _ in range(30):                       # settle on the exact profile, then one step in the profile under test
+                gcfg.math = bb.BH_MATH_EXACT; sim.set_params(gcfg); sim.step(float(DT), 1)
+            gcfg.math = math; sim.set_params(gcfg)
+            sim.step(float(DT), 1)
+            out[math], _, _ = sim.download()
+    err = rel_err(out[bb.BH_MATH_FAST], out[bb.BH_MATH_EXACT])
+    assert np.percentile(err, 99.9) <= 1e-5, f"p99.9 {np.percentile(err, 99.9):.3e}"
+
+
 # ---- BASELINE.json sizes: size-independent properties + sampled strands against the oracle -------------
 
 def _sample_strands(pos, vel, S, N, idx):
