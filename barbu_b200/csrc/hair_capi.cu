@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -149,6 +150,7 @@ int bh_destroy(bh_sim* s) {
   cudaFree(s->skin_rest3); cudaFree(s->skin_joints4); cudaFree(s->skin_weights3); cudaFree(s->skin_dq);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : s->host_events) cudaEventDestroy(ev);
   delete s;
   return BH_OK;
 }
@@ -342,35 +344,52 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
   if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_step_host: buffer 0 is a GL buffer");
   DeviceGuard g(s->device);
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
-  // Strands are independent, so a slice of strands can be uploaded, stepped `substeps` times and
-  // downloaded while its neighbours are still in flight: H2D, kernels and D2H of different slices
-  // overlap on kHostPipeStreams streams (PCIe is full duplex).
+  // Strands are independent, so a slice of strands can be uploaded, stepped `substeps` times and downloaded while its
+  // neighbours are still in flight. Three streams, one per engine — pipe[0] uploads, pipe[1] runs the kernels, pipe[2]
+  // downloads — chained per slice by events, so no download ever waits behind an upload of a later slice (PCIe is full
+  // duplex) and the only serial parts of a call are the first upload and the last download.
+  // 16 slices measured best at configs[1] (profiles/r01_e2e_slices.txt): fewer lengthen the serial first upload / last
+  // download, more add per-slice costs.
   const int64_t S = s->nstrands;
-  int64_t slice = (S + 31) / 32;
-  const int64_t min_slice = 4096;
-  if (slice < min_slice) slice = min_slice;
-  slice = (slice + 127) / 128 * 128;
+  static const int nslices = [] { const char* e = getenv("BH_HOST_SLICES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();   // tuning knob
+  std::vector<int64_t> bounds;                                              // slice k = [bounds[k], bounds[k + 1])
+  {
+    int64_t slice = (S + nslices - 1) / nslices;
+    if (slice < 4096) slice = 4096;
+    slice = (slice + 127) / 128 * 128;                                      // whole 32-strand tiles, even strand counts
+    for (int64_t x = 0; x < S; x += slice) bounds.push_back(x);
+    bounds.push_back(S);
+  }
+  const int64_t count_slices = (int64_t)bounds.size() - 1;
+  while ((int64_t)s->host_events.size() < 2 * count_slices + 1) {
+    cudaEvent_t ev;
+    BH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    s->host_events.push_back(ev);
+  }
+  cudaStream_t up = s->pipe[0], run = s->pipe[1], down = s->pipe[2];
   // order after whatever is queued on the sim's stream
-  cudaEvent_t ev;
-  BH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  cudaError_t e = cudaEventRecord(ev, s->stream);
-  for (int i = 0; i < kHostPipeStreams && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s->pipe[i], ev, 0);
-  int k = 0;
-  for (int64_t first = 0; first < S && e == cudaSuccess; first += slice, ++k) {
-    const int64_t count = (S - first < slice) ? (S - first) : slice;
-    cudaStream_t st = s->pipe[k % kHostPipeStreams];
+  cudaEvent_t ev0 = s->host_events[2 * count_slices];
+  cudaError_t e = cudaEventRecord(ev0, s->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(up, ev0, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(run, ev0, 0);
+  for (int64_t k = 0; k < count_slices && e == cudaSuccess; ++k) {
+    const int64_t first = bounds[k], count = bounds[k + 1] - bounds[k];
     const size_t off = (size_t)first * s->nverts, bytes = (size_t)count * s->nverts * sizeof(float4);
     float4* dP = s->planes[BH_PLANE_POSITION] + off;
     float4* dV = s->planes[BH_PLANE_VELOCITY] + off;
-    e = cudaMemcpyAsync(dP, pos4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, vel4 + 4 * off, bytes, cudaMemcpyHostToDevice, st);
+    cudaEvent_t uploaded = s->host_events[2 * k], stepped = s->host_events[2 * k + 1];
+    e = cudaMemcpyAsync(dP, pos4 + 4 * off, bytes, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, vel4 + 4 * off, bytes, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaEventRecord(uploaded, up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(run, uploaded, 0);
     const bh::StepArgs a = make_args(s, h, dP, dV, count);
-    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, st, s->tile_counters + 32 * (k % kHostPipeStreams)); s->launches += 1; }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(vel4 + 4 * off, dV, bytes, cudaMemcpyDeviceToHost, st);
+    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+    if (e == cudaSuccess) e = cudaEventRecord(stepped, run);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(down, stepped, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, down);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vel4 + 4 * off, dV, bytes, cudaMemcpyDeviceToHost, down);
   }
-  for (int i = 0; i < kHostPipeStreams; ++i) { cudaError_t e2 = cudaStreamSynchronize(s->pipe[i]); if (e == cudaSuccess) e = e2; }
-  cudaEventDestroy(ev);
+  for (int i = 0; i < 3; ++i) { cudaError_t e2 = cudaStreamSynchronize(s->pipe[i]); if (e == cudaSuccess) e = e2; }
   if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_step_host", e); }
   s->initialized = true;
   return BH_OK;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace bh {
 
 constexpr int kHostPipeStreams = 4;
@@ -44,6 +46,7 @@ struct bh_sim {
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
   int64_t launches = 0;
+  std::vector<cudaEvent_t> host_events;  // bh_step_host: two per slice + one, created on first use
   unsigned int* tile_counters = nullptr;  // kHostPipeStreams + 1 words: one tile scheduler per stream that may be in flight
   // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)
   float* root_pos3 = nullptr;

@@ -132,12 +132,33 @@ def cpu_reference_time(nstrands_sample, steps, warmup, threads):
     return nstrands_sample * NVERTS * SUBSTEPS * steps / dt, dt / steps
 
 
+def reference_source_time(nstrands_sample):
+    """The reference's own shader SOURCE (oracle/_ref: cs_simulation.glsl compiled as C++ over the reference's GLM, one
+    fiber per invocation, OpenMP over workgroups) on a small sample: one frame of 4 substeps. Reported beside the
+    restatement; it is NOT the arm's value — its time is dominated by the fiber switches that emulate the workgroup
+    barriers (~100x slower than the restatement, which computes the same bits), so using it would inflate every ratio."""
+    from oracle import pyoracle as po
+    if not po.ref_available(NVERTS):
+        return None
+    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU)
+    root_pos, root_nrm = root_pos[:nstrands_sample], root_nrm[:nstrands_sample]
+    pos, vel = po.init_strands(root_pos, root_nrm, po.random_values(SEED, nstrands_sample), NVERTS)
+    h = float(np.float32(DT) / np.float32(SUBSTEPS))
+    po.ref_update(pos, vel, nstrands_sample, NVERTS, h, SCALE, SPHERE)   # warm-up (fiber stacks, page faults)
+    t0 = time.perf_counter()
+    for _ in range(SUBSTEPS):
+        po.ref_update(pos, vel, nstrands_sample, NVERTS, h, SCALE, SPHERE)
+    return nstrands_sample * NVERTS * SUBSTEPS / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
     sample = 1 << 17                                                     # 1/8 of the per-GPU workload per step
     value, s_per_step = cpu_reference_time(sample, args.steps, args.warmup, threads)
+    src_sample = 1 << 12
+    src_value = reference_source_time(src_sample)
     sample_txt = (f"first {sample} of {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices x {SUBSTEPS} substeps per step, "
                   f"{threads} OpenMP threads")
     line = {
@@ -150,6 +171,10 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_source": {"value": src_value, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"first {src_sample} strands x {NVERTS} vertices x {SUBSTEPS} substeps, 1 step",
+                             "note": "oracle/_ref: the reference shader source itself on the CPU (fiber per invocation); "
+                                     "bit-identical results to the restatement timed above, reported for completeness"},
     }
     print(json.dumps(line))
 
