@@ -534,3 +534,61 @@ def test_full_size_step_host_round_trip_equals_device_resident():
         sim.step_host(float(DT), 4, hp, hv)
     assert_bit_equal(hp.reshape(-1, 4), want_p, "positions through host buffers")
     assert_bit_equal(hv.reshape(-1, 4), want_v, "velocities through host buffers")
+
+
+def test_config3_shape_skinned_roots_and_capsules_sampled_parity():
+    """configs[2] of BASELINE.json in shape (extension: oracle-defined, no reference parity): sphere scalp skinned by an
+    8-joint dual-quaternion palette re-posed every frame, sphere + 2 capsule colliders, 4 substeps per frame — here at
+    2^20 strands x 32 (tools/config3.py runs the 4M-strand size). Whole tiles of strands are replayed on the CPU oracle
+    and must match bit for bit; no free vertex may end inside a collider."""
+    rows, cols, N, J, frames, substeps = 1024, 1024, 32, 8, 3, 4
+    S = rows * cols
+    caps = CAPSULE_SETS["arms"]
+    root_pos, root_nrm, _ = po.sphere_scalp(rows, cols)
+    jy = np.linspace(-1.0, 1.0, J, dtype=np.float32)
+    d = np.abs(root_pos[:, 1:2] - jy[None, :])
+    joints = np.argsort(d, axis=1)[:, :4].astype(np.int32)
+    w = 1.0 / (np.take_along_axis(d, joints, 1) + 0.05)
+    weights = np.ascontiguousarray((w / w.sum(1, keepdims=True)).astype(np.float32)[:, :3])
+
+    def palette(frame):
+        out = np.zeros((J, 8), np.float32)
+        for j in range(J):
+            a = 0.05 * np.sin(0.35 * frame + 0.7 * j)
+            tx = 0.02 * np.sin(0.2 * frame + j)
+            qz, qw = np.sin(a / 2), np.cos(a / 2)
+            out[j] = (0.0, 0.0, qz, qw, 0.5 * tx * qw, -0.5 * tx * qz, 0.0, 0.0)   # real xyzw, dual = 0.5 * t * q
+        return out
+
+    par, gcfg = _capsule_params(caps, dt=float(np.float32(DT) / np.float32(substeps)), scale=1.45, sphere=SPHERE)
+    tiles = np.unique(np.concatenate([[0, S // 32 - 1], np.arange(0, S // 32, 257)]))
+    idx = (tiles[:, None] * 32 + np.arange(32)).ravel()
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        assert sim.kernel_kind == 0
+        sim.init_sphere_scalp(rows, cols, 0, bb.random_values(1234, 0, S))
+        sim.set_skin(root_pos, joints, weights)
+        pos0, vel0, _ = sim.download()
+        p, v = _sample_strands(pos0, vel0, S, N, idx)
+        for f in range(frames):
+            dq = palette(f)
+            sim.skin_roots(dq)
+            sim.step(float(DT), substeps)
+            sp, _ = po.skin_roots_dq(root_pos[idx], root_nrm[idx], joints[idx], weights[idx], dq)
+            p.reshape(-1, N, 4)[:, 0, :3] = sp
+            for _ in range(substeps):
+                po.step(p, v, idx.size, N, par, nthreads=16)
+        pos1, vel1, _ = sim.download()
+    gp, gv = _sample_strands(pos1, vel1, S, N, idx)
+    assert_bit_equal(gp, p, "sampled positions")
+    assert_bit_equal(gv, v, "sampled velocities")
+    assert_bit_equal(pos1[:, 3], pos0[:, 3], "I4 rest lengths")
+    x = pos1[:, :3].astype(np.float64).reshape(S, N, 3)[:, 1:].reshape(-1, 3)
+    x = x[np.isfinite(x).all(axis=1)]
+    # the LAST collider always leaves its vertices on its surface; earlier ones may be re-entered by a later push-out
+    a, b, r = (np.array(t, np.float64) for t in caps[-1])
+    ab = b - a
+    t = np.clip((x - a) @ ab / (ab @ ab), 0.0, 1.0)
+    dist = np.linalg.norm(x - (a + t[:, None] * ab), axis=1)
+    assert dist.min() >= float(r) * (1 - 1e-5), "vertex inside the last capsule"
+    assert (np.abs(dist - float(r)) < 1e-5).any(), "nothing rests on the capsule: the case does not cover it"

@@ -32,7 +32,7 @@ if os.path.exists(lf):
             k = r[ik].split("(")[0][-70:]
             ns = float(r[iv].replace(",", ""))
             if "hair_step" in k:      # the same kernel runs on the whole shard (timed region) and on 1/32 slices (bh_step_host leg)
-                k += "  [whole shard, 2^20 strands]" if ns > 2e5 else "  [bh_step_host slice, 2^15 strands]"
+                k += "  [whole shard, 2^20 strands]" if ns > 2e5 else "  [bh_step_host slice, 2^16 strands]"
             tot[k] += ns; cnt[k] += 1
     s = sum(tot.values())
     with open(os.path.join(P, f"{rnd}_ncu_launches_summary.txt"), "w") as f:
