@@ -300,6 +300,13 @@ class HairSim:
         _check(self._lib.bh_download(self._h, *[_ptr(a) for a in outs]))
         return tuple(outs)
 
+    def download_into(self, pos4=None, vel4=None, tan4=None):
+        """bh_download into caller-owned float32 arrays (e.g. PinnedBuffer.array): no allocation, no staging copy."""
+        for a in (pos4, vel4, tan4):
+            if a is not None and (a.dtype != np.float32 or not a.flags.c_contiguous or a.size != 4 * self.nvertices):
+                raise ValueError("download_into: need C-contiguous float32 arrays of 4 * nvertices elements")
+        _check(self._lib.bh_download(self._h, _ptr(pos4), _ptr(vel4), _ptr(tan4)))
+
     def device_plane(self, plane: int):
         ptr, nbytes = C.c_void_p(), C.c_uint64()
         _check(self._lib.bh_device_plane(self._h, plane, C.byref(ptr), C.byref(nbytes)))

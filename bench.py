@@ -270,7 +270,7 @@ def run_gpu(args, rank, world, local_rank):
         sim.configure(math=math)
 
     # ---- end to end through the C ABI with HOST buffers (bh_step_host): H2D + 4 substeps + D2H per step ---
-    e2e_value, e2e_steps = None, 0
+    e2e_value, e2e_resident, e2e_steps = None, None, 0
     if not args.no_e2e:
         hp, hv = bb.PinnedBuffer(4 * V), bb.PinnedBuffer(4 * V)
         p0, v0, _ = sim.download()
@@ -289,6 +289,21 @@ def run_gpu(args, rank, world, local_rank):
         if dist is not None:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e_value = world * V * SUBSTEPS * e2e_steps / float(t_e2e.item())
+        # Second flavour, reported beside it: the reference's own call pattern. Hair::update(dt) takes no buffers — the
+        # state lives in the module's GL buffer — so per frame the host sends the uniforms (bounding sphere, dt) and a
+        # host-side consumer reads the position plane back.
+        sim.upload(hp.array, hv.array)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sim.set_bounding_sphere(SPHERE)
+            sim.step(DT, SUBSTEPS)
+            sim.download_into(pos4=hp.array)
+        torch.cuda.synchronize()
+        t_res = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        e2e_resident = world * V * SUBSTEPS * e2e_steps / float(t_res.item())
         hp.free(); hv.free()
 
     # ---- optional exchange step (N > 1): all-gather of the position plane to every rank, NCCL over NVLink ----------
@@ -338,6 +353,9 @@ def run_gpu(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V, "ms_per_launch": per_launch_s * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * V, "d2h_bytes_per_step": 32 * V,
                     "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)"},
+            "e2e_resident_state": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 16 * V,
+                                   "steps": e2e_steps, "api": "bh_set_bounding_sphere + bh_step + bh_download(position plane): the "
+                                   "reference's Hair::update call pattern, state resident on the device, positions read back to pinned host memory"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
