@@ -26,12 +26,19 @@ constexpr unsigned long long kGolden = 0x9E3779B97F4A7C15ull;
 __global__ void __launch_bounds__(256) checksum_kernel(const uint4* __restrict__ plane, long long nvertices,
                                                        unsigned long long key0, unsigned long long* __restrict__ out) {
   unsigned long long c0 = 0, c1 = 0;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvertices; v += (long long)gridDim.x * blockDim.x) {
-    const uint4 w = __ldg(plane + v);
+  auto add = [&](const uint4 w, const long long v) {
     const unsigned long long k = (key0 + 4ull * (unsigned long long)v + 1ull) * kGolden;   // key of .x, already multiplied
     c0 += (unsigned long long)w.x + w.y + w.z + w.w;
     c1 += w.x * k + w.y * (k + kGolden) + w.z * (k + 2 * kGolden) + w.w * (k + 3 * kGolden);
+  };
+  // four independent 16-byte loads in flight per thread (a read-only stream: latency is hidden by loads, not by warps)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; v + 3 * stride < nvertices; v += 4 * stride) {
+    const uint4 w0 = __ldcs(plane + v), w1 = __ldcs(plane + v + stride), w2 = __ldcs(plane + v + 2 * stride), w3 = __ldcs(plane + v + 3 * stride);
+    add(w0, v); add(w1, v + stride); add(w2, v + 2 * stride); add(w3, v + 3 * stride);
   }
+  for (; v < nvertices; v += stride) add(__ldcs(plane + v), v);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     c0 += __shfl_xor_sync(0xffffffffu, c0, d);
