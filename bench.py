@@ -102,6 +102,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": window, "power_w_max": max(pw) if pw else None}
 
 
+_emit_fd = None
+
+
+def emit(text):
+    """The one line of the bench contract, on the process's original stdout."""
+    data = (text + "\n").encode()
+    if _emit_fd is None:
+        sys.stdout.write(text + "\n"); sys.stdout.flush()
+    else:
+        os.write(_emit_fd, data)
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -176,7 +188,7 @@ def run_reference(args, rank, world):
                              "note": "oracle/_ref: the reference shader source itself on the CPU (fiber per invocation); "
                                      "bit-identical results to the restatement timed above, reported for completeness"},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -384,7 +396,7 @@ def run_gpu(args, rank, world, local_rank):
                                              "fast = FMA-contracted + MUFU.RSQ arithmetic (<= 1e-5 relative per vertex after one step)"}
         if gather is not None:
             line["allgather"] = gather
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -413,10 +425,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that print there on their own (NCCL's version banner does)
+    # are sent to stderr for the duration of the run; emit() writes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit_fd
+    _emit_fd = real_stdout
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_gpu(args, rank, world, local_rank)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
