@@ -35,7 +35,9 @@ SEED = 1234
 
 
 def workload_name(n_gpus):
-    return (f"configs[1]: synthetic sphere scalp, {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices per GPU, "
+    tag = "configs[1]" if ROWS * COLS_PER_GPU == 1 << 20 else \
+          ("configs[3] (64M strands over 8 GPUs) shard size" if ROWS * COLS_PER_GPU == 1 << 23 else "configs[1] at another shard size")
+    return (f"{tag}: synthetic sphere scalp, {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices per GPU, "
             f"{SUBSTEPS} substeps/frame, sphere collider r=0.98, scale {SCALE}, dt 1/90")
 
 
@@ -358,7 +360,7 @@ def run_gpu(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(world), "math": args.math, "iterations": 8,
                        "state": f"settled: {args.settle} untimed frames from the cold state, then {args.warmup}+ warm-up steps",
-                       "l2": "state 1 GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
+                       "l2": f"state {32 * V / 2**30:g} GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": kernel_names.get(kernel_kind, "?"), "peak_source": peak_src,
@@ -382,6 +384,8 @@ def run_gpu(args, rank, world, local_rank):
         if os.path.exists(traffic_file):
             with open(traffic_file) as f:
                 traffic = json.load(f)
+        if S != 1 << 20:
+            traffic = {}                                      # the ncu capture is of the configs[1] launch
         line["roofline"]["traffic"] = traffic.get(args.math)
         if other is not None:
             ms2, launches2, clocks2 = other
@@ -420,8 +424,13 @@ def main():
                     help="untimed frames run before the W warm-up steps so that the timed region sees the SETTLED hair (strands "
                          "draped over the collider, push-outs in ~40%% of warp-steps), not the cold straight state, which is "
                          "cheaper for the exact profile (0 for profiler runs that want the cold state)")
+    ap.add_argument("--log2-strands", type=int, default=20,
+                    help="strands per GPU = 2^k (default 20 = configs[1]; 23 = the per-GPU shard of configs[3], 64M strands over 8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    global ROWS, COLS_PER_GPU
+    ROWS = 1 << (args.log2_strands // 2)
+    COLS_PER_GPU = (1 << args.log2_strands) // ROWS
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
