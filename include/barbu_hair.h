@@ -140,7 +140,7 @@ int  bh_skin_roots(bh_sim* sim, const float* dq_palette, int njoints);
 /* ---- next stage: the tess-stream pass of Hair::render (hair.cc:141-173) on the device ------------ */
 /* Interpolated render strands as the GL_LINES vertex stream (xyz, relPos) that glDrawTransformFeedback consumes:
  * per patch (6 control points, bh_build_patch_indices order), instance, isoline and sub-segment two float4.
- * Formulas of shaders/hair/02_tess_stream/*.glsl + shared/inc_maths.glsl (hermite_mix, sample_triangle2, smoothstep2);
+ * Formulas of shaders/hair/02_tess_stream/ (all four stages) + shared/inc_maths.glsl (hermite_mix, sample_triangle2, smoothstep2);
  * tess coordinates, primitive order and the (seeded, counter-based) random pair are defined by this library because
  * the reference leaves them to the GL implementation / to std::random_device: no reference parity is claimed there. */
 typedef struct bh_tess_params { int ninstances; int nlines; int nsubsegments; unsigned seed; } bh_tess_params;   /* hair.h:32-36 */
