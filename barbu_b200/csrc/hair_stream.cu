@@ -182,7 +182,12 @@ struct Pipe {
   bool heldCap;    // capsule variant, warp-uniform: that vertex went through the capsule chain -> recompute it with its velocity
 };
 
-template <class PM> __device__ __noinline__ u64 neg_inversesqrt_slow(u64 x) { return PM::neg_inversesqrt_ieee(x); }
+struct Quad { u64 v[4]; };
+template <class PM> __device__ __noinline__ Quad neg_inversesqrt_slow(Quad x) {
+#pragma unroll 1
+  for (int a = 0; a < 4; ++a) x.v[a] = PM::neg_inversesqrt_ieee(x.v[a]);
+  return x;
+}
 
 // ninv[a] = -inversesqrt(x[a]). The branch-free sequence is issued unconditionally; when some lane of the warp has an
 // operand outside its range (`ok` false: rare), the whole warp recomputes with the IEEE builtins.
@@ -191,8 +196,9 @@ __device__ __forceinline__ void neg_inversesqrt_batch(const u64 (&x)[4], u64 (&n
 #pragma unroll
   for (int a = 0; a < 4; ++a) ninv[a] = PM::neg_inversesqrt_in_range(x[a], nz);
   if (PM::kRangeChecked && !__all_sync(0xffffffffu, ok)) {
+    const Quad r = neg_inversesqrt_slow<PM>(Quad{ { x[0], x[1], x[2], x[3] } });
 #pragma unroll
-    for (int a = 0; a < 4; ++a) ninv[a] = neg_inversesqrt_slow<PM>(x[a]);
+    for (int a = 0; a < 4; ++a) ninv[a] = r.v[a];
   }
 }
 
