@@ -6,9 +6,9 @@ synthetic stand-in SURVEY §8d defines: sphere scalp 2048 x 2048, an 8-joint cha
 re-posed every frame, roots skinned on the device (bh_skin_roots), sphere + 2 capsule colliders, 4 substeps per frame.
 EXTENSION CONFIG: no reference parity exists; the check below is against the CPU oracle on sampled strands.
 
-Prints one JSON line per arithmetic profile. Usage: python tools/config3.py [--log2s 22] [--frames 10] [--check 2048]"""
+Prints one JSON line per arithmetic profile. Usage: python tests/reports/config3.py [--log2s 22] [--frames 10] [--check 2048]"""
 import argparse, json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import barbu_b200 as bb
 
@@ -20,7 +20,7 @@ ap.add_argument("--check", type=int, default=2048, help="strands compared bit-fo
 ap.add_argument("--caps", default="arms", choices=["arms", "far", "none"], help="far: capsules nothing can reach (cost of the bound test alone)")
 ap.add_argument("--math", default="both", choices=["both", "exact", "fast"])
 args = ap.parse_args()
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
 S, N, SUB, J = 1 << args.log2s, 32, 4, 8

@@ -4,7 +4,7 @@ Runs config 1 (4,096 strands x 16) and 4,096 x 32 for 100 steps on the GPU in bo
 the CPU oracle (test infrastructure) after 1, 10, 50 and 100 steps: max / p99.9 / p99 / median relative position error
 and the fraction of vertices within 1e-5 (error measure of SURVEY.md App. B). The exact profile must be bit-identical."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import barbu_b200 as bb
 from oracle import pyoracle as po

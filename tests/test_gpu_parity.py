@@ -539,7 +539,7 @@ def test_full_size_step_host_round_trip_equals_device_resident():
 def test_config3_shape_skinned_roots_and_capsules_sampled_parity():
     """configs[2] of BASELINE.json in shape (extension: oracle-defined, no reference parity): sphere scalp skinned by an
     8-joint dual-quaternion palette re-posed every frame, sphere + 2 capsule colliders, 4 substeps per frame — here at
-    2^20 strands x 32 (tools/config3.py runs the 4M-strand size). Whole tiles of strands are replayed on the CPU oracle
+    2^20 strands x 32 (tests/reports/config3.py runs the 4M-strand size). Whole tiles of strands are replayed on the CPU oracle
     and must match bit for bit; no free vertex may end inside a collider."""
     rows, cols, N, J, frames, substeps = 1024, 1024, 32, 8, 3, 4
     S = rows * cols
