@@ -1,0 +1,34 @@
+"""compute-sanitizer workload: every streaming-kernel variant (N = 32 / 8 / 4, off-origin sphere, capsules, both profiles) checked
+against the oracle, plus generation, tess-stream and checksum kernels, at sizes the sanitizer finishes in seconds.
+Usage on the GPU box: compute-sanitizer --tool {memcheck,racecheck,initcheck,synccheck} python tests/reports/sanitizer_case.py"""
+import numpy as np, sys
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import barbu_b200 as bb
+from oracle import pyoracle as po
+from tests.util import DT, SPHERE, ragged_state, assert_bit_equal
+# small shapes through every streaming variant: N=32 (root + inner chunks), N=8, N=4 (two strands per row), capsules, off-origin sphere
+for (S, N, sphere, caps) in [(100, 32, SPHERE, 0), (70, 8, (0.1, 0.0, 0.05, 0.95), 0), (130, 4, (0, 0, 0, 1.02), 0), (90, 16, SPHERE, 2)]:
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=sphere, ncapsules=caps)
+    g = bb.default_params(); g.scale = 1.45; g.ncapsules = caps
+    for i, x in enumerate(sphere): g.sphere[i] = x
+    for q in range(caps):
+        a, b, r = ((0.5, 0.3, 0.0), (1.2, -0.3, 0.0), 0.3) if q == 0 else ((0.0, 1.0, 0.0), (0.3, 1.4, 0.2), 0.25)
+        for i in range(3): par.capsules[q].a[i] = g.capsules[q].a[i] = a[i]; par.capsules[q].b[i] = g.capsules[q].b[i] = b[i]
+        par.capsules[q].radius = g.capsules[q].radius = r
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(6): po.step(rp, rv, S, N, par)
+    for math in (bb.BH_MATH_EXACT, bb.BH_MATH_FAST):
+        g.math = math
+        with bb.HairSim(S, N) as sim:
+            sim.set_params(g); sim.upload(pos, vel)
+            for _ in range(6): sim.step(float(DT), 1)
+            gp, gv, _ = sim.download()
+        if math == bb.BH_MATH_EXACT:
+            assert_bit_equal(gp, rp); assert_bit_equal(gv, rv)
+    print("ok", S, N, caps, flush=True)
+# tess-stream + checksum + generation kernels
+sim = bb.HairSim(64 * 64, 16); sim.configure(scale=1.45, sphere=SPHERE)
+sim.init_sphere_scalp(64, 64, 0, bb.random_values(1, 0, 64 * 64))
+tri = bb.sphere_scalp_triangles(64, 64); sim.tess_set_patches(bb.build_patch_indices(tri, 16))
+out = sim.tess_stream(3, 2, 16, 7); print("tess", out.shape, sim.checksum(3)); sim.close()
