@@ -592,3 +592,24 @@ def test_config3_shape_skinned_roots_and_capsules_sampled_parity():
     dist = np.linalg.norm(x - (a + t[:, None] * ab), axis=1)
     assert dist.min() >= float(r) * (1 - 1e-5), "vertex inside the last capsule"
     assert (np.abs(dist - float(r)) < 1e-5).any(), "nothing rests on the capsule: the case does not cover it"
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 8, 16, 32, 64, 128])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_states_bit_exact(N, seed):
+    """The randomised states of tests/test_oracle_vs_reference_live.py (gentle / rough / violent, three spheres, three
+    time steps and scales) on the device: every kernel choice (streaming, per-strand) against the oracle, bit for bit."""
+    from tests.test_oracle_vs_reference_live import random_state
+    rng = np.random.default_rng(1000 * N + seed)
+    S = 1500
+    pos, vel = random_state(rng, S, N, [0.02, 0.3, 2.0][seed])
+    sphere = [(0.0, 0.0, 0.0, 0.98), (0.1, -0.2, 0.05, 1.1), (0.0, 0.5, 0.0, 0.6)][seed]
+    scale = [1.0, 1.45, 0.7][seed]
+    dt = float(np.float32(1.0) / np.float32(90.0)) * [1.0, 0.25, 2.0][seed]
+    par = po.default_params(dt=dt, scale=scale, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(6):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    gp, gv = gpu_steps(pos, vel, S, N, 6, dt=dt, scale=scale, sphere=sphere)
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")

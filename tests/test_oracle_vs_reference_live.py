@@ -1,0 +1,72 @@
+"""The oracle against the reference shader SOURCE executed here (oracle/_ref: cs_simulation.glsl compiled over the reference's
+GLM) on RANDOMISED states — beyond the committed golden shapes: random roots and velocities, spheres on and
+off the origin, contacts from the first step, degenerate segments (NaN by the reference's own arithmetic), special values.
+Bit-exact. Skipped where oracle/_ref was not built (it needs the reference checkout; the committed fixtures still pin the
+oracle there)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import assert_bit_equal
+
+NVERTS = [2, 3, 4, 8, 16, 32, 64, 128]
+
+
+def random_state(rng, S, N, spread):
+    root = rng.standard_normal((S, 3)).astype(np.float32)
+    root /= np.linalg.norm(root, axis=1, keepdims=True).astype(np.float32)
+    nrm = root + (rng.standard_normal((S, 3)) * spread).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    rv = (1.0 + 0.1 * (1.0 - 2.0 * rng.random(S))).astype(np.float32)
+    pos, vel = po.init_strands(root, nrm.astype(np.float32), rv, N)
+    vel[:, :3] = (rng.standard_normal((S * N, 3)) * spread).astype(np.float32)
+    pos[:, :3] += (rng.standard_normal((S * N, 3)) * spread * 0.05).astype(np.float32)
+    return pos, vel
+
+
+@pytest.mark.parametrize("N", NVERTS)
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_states_bit_exact_vs_reference_shader(N, seed):
+    if not po.ref_available(N):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(1000 * N + seed)
+    S = 48
+    spread = [0.02, 0.3, 2.0][seed]                                    # gentle, rough, violent
+    pos, vel = random_state(rng, S, N, spread)
+    sphere = [(0.0, 0.0, 0.0, 0.98), (0.1, -0.2, 0.05, 1.1), (0.0, 0.5, 0.0, 0.6)][seed]
+    scale = [1.0, 1.45, 0.7][seed]
+    dt = float(np.float32(1.0) / np.float32(90.0)) * [1.0, 0.25, 2.0][seed]
+    par = po.default_params(dt=dt, scale=scale, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for it in range(6):
+        po.step(pos, vel, S, N, par)
+        po.ref_update(rp, rv, S, N, dt, scale, sphere)
+        assert_bit_equal(pos, rp, f"positions after {it + 1} updates")
+        assert_bit_equal(vel, rv, f"velocities after {it + 1} updates")
+
+
+@pytest.mark.parametrize("N", [4, 8, 32])
+def test_degenerate_and_special_values_bit_exact_vs_reference_shader(N):
+    """Zero-length segments (normalize(0) -> NaN in the reference's arithmetic), a vertex at the sphere centre, -0.0,
+    huge and denormal coordinates, infinite velocity: the oracle must produce what the shader source produces."""
+    if not po.ref_available(N):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(77 + N)
+    S = 16
+    pos, vel = random_state(rng, S, N, 0.05)
+    P = pos.reshape(S, N, 4); V = vel.reshape(S, N, 4)
+    P[0, 1, :3] = P[0, 0, :3]                                          # coincident with the root: vdiff = 0
+    P[1, N - 1, :3] = 0.0                                              # at the sphere centre: inversesqrt(0)
+    P[2, 1, :3] = -0.0
+    P[3, 1, :3] = 1.0e19; P[3, N - 1, :3] = -3.0e38                    # dot overflows to inf
+    P[4, 1, :3] = P[4, 0, :3] + np.float32(1e-30)                      # denormal-range squared length
+    V[5, 1, :3] = np.inf; V[6, N - 1, 0] = np.nan
+    P[7, :, 3] = 0.0                                                   # zero rest lengths
+    P[8, 1:, :3] = P[8, 0, :3]                                         # a whole strand collapsed onto its root
+    par = po.default_params(dt=float(np.float32(1.0) / np.float32(90.0)), scale=1.45, sphere=(0.0, 0.0, 0.0, 0.98))
+    rp, rv = pos.copy(), vel.copy()
+    for it in range(3):
+        po.step(pos, vel, S, N, par)
+        po.ref_update(rp, rv, S, N, par.dt, 1.45, (0.0, 0.0, 0.0, 0.98))
+        assert_bit_equal(pos, rp, f"positions after {it + 1} updates")
+        assert_bit_equal(vel, rv, f"velocities after {it + 1} updates")
