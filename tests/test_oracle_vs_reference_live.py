@@ -70,3 +70,35 @@ def test_degenerate_and_special_values_bit_exact_vs_reference_shader(N):
         po.ref_update(rp, rv, S, N, par.dt, 1.45, (0.0, 0.0, 0.0, 0.98))
         assert_bit_equal(pos, rp, f"positions after {it + 1} updates")
         assert_bit_equal(vel, rv, f"velocities after {it + 1} updates")
+
+
+@pytest.mark.parametrize("N", [2, 4, 16, 128])
+@pytest.mark.parametrize("seed", [3, 99, 123456])
+def test_host_generation_bit_exact_vs_reference_host_code(N, seed):
+    """Hair::init_simulation (hair.cc:236-361: jitter by glibc rand(), rest lengths, tangents with glm::simplex) and
+    Hair::init_mesh's element loop (hair.cc:397-409), sliced from the reference's hair.cc and run live, on random scalps."""
+    if not po.ref_available(N):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(seed)
+    S = 40
+    root = (rng.standard_normal((S, 3)) * 3.0).astype(np.float32)
+    nrm = rng.standard_normal((S, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    maxlength = float(np.float32(rng.uniform(0.1, 2.0)))
+    rpos, rvel, rtan = po.ref_init_simulation(root, nrm, seed, N, maxlength)
+    pos, vel = po.init_strands(root, nrm, po.random_values(seed, S), N, maxlength)
+    assert_bit_equal(pos, rpos, "positions + rest lengths")
+    assert_bit_equal(vel, rvel, "velocities")
+    assert_bit_equal(po.init_tangents(nrm, N, maxlength), rtan, "tangents")
+    tri = rng.integers(0, S, (25, 3)).astype(np.int32)
+    assert_bit_equal(po.patch_indices(tri, N), po.ref_patch_indices(tri, S, N), "patch indices")
+
+
+def test_simplex_noise_bit_exact_vs_glm_live():
+    if not po.ref_available(4):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(5)
+    o = po.oracle()
+    for x, y in (rng.standard_normal((500, 2)) * 37.0).astype(np.float32):
+        a, b = np.float32(o.bho_simplex2(float(x), float(y))), np.float32(po.ref_simplex2(float(x), float(y)))
+        assert a.view(np.uint32) == b.view(np.uint32), (x, y, a, b)
