@@ -579,8 +579,15 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
   const cuuint64_t strides[1] = { (cuuint64_t)nverts * 16 };
   const cuuint32_t box[2] = { 32, 32 };
   const cuuint32_t estr[2] = { 1, 1 };
+  // L2 promotion: a tile row of >= 1 KB (64+ vertices per strand) gives every 128-byte piece of a box its own DRAM page, and
+  // fetching 256 B per request halves the page openings (+5 % measured at 64 and 128 vertices per strand); with short rows
+  // the box is (nearly) contiguous and 256 B costs bandwidth (-16 % at the reference's 4 vertices per strand).
+  static const int promo_env = [] { const char* e = getenv("BH_TMA_L2_PROMOTION"); return e ? atoi(e) : -1; }();   // tuning knob: 0, 64, 128, 256
+  const int promo = promo_env >= 0 ? promo_env : (nverts >= 64 ? 256 : 128);
+  const CUtensorMapL2promotion l2 = promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                    promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct DeviceInfo { int sms = 0; bool ready[12] = {}; int blocks_per_sm[12] = {}; };
