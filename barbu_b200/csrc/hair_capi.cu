@@ -330,10 +330,15 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   DeviceGuard g(s->device);
   int rc = map_gl(s); if (rc) return rc;
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
-  const bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
+  bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
+  static const bool zigzag = [] { const char* e = getenv("BH_NO_ZIGZAG"); return !(e && e[0] == '1'); }();
   for (int q = 0; q < substeps; ++q) {
+    // Consecutive launches walk the shard in opposite directions: a launch starts with the tiles the previous one wrote
+    // last, which are still in the 126 MB L2 — those reads, and the write-backs they replace, never reach HBM.
+    a.reverse = zigzag ? (int)(s->step_launches & 1) : 0;
     BH_CUDA(bh::launch_step(a, s->params.math, s->stream, s->tile_counters + 32 * kHostPipeStreams));
     s->launches += 1;
+    s->step_launches += 1;
   }
   return unmap_gl(s);
 }

@@ -46,6 +46,7 @@ struct bh_sim {
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
   int64_t launches = 0;
+  int64_t step_launches = 0;             // launches of bh_step alone: parity = tile direction of the next one
   std::vector<cudaEvent_t> host_events;  // bh_step_host: two per slice + one, created on first use
   unsigned int* tile_counters = nullptr;  // kHostPipeStreams + 1 words: one tile scheduler per stream that may be in flight
   // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)

@@ -24,6 +24,7 @@ struct StepArgs {
   float keep;             // 1 - drag (extension)
   int use_drag;
   int ncaps;
+  int reverse;            // streaming kernel: hand the tiles out from the last one down (see bh_step: alternates per launch)
   Capsule caps[kMaxCapsules];
   // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
   // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.

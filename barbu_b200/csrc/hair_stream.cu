@@ -469,7 +469,8 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     unsigned int t = 0;
     if (lane == 0) t = atomicAdd(tile_counter, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    return t < ntiles ? (int)t : -1;
+    if (t >= ntiles) return -1;
+    return (int)(a.reverse ? ntiles - 1u - t : t);                            // strands are independent: any tile order is the same result
   };
   auto issue_load = [&](int tile, int c, int b) {                           // lane 0 only
     const uint32_t bar = bar_s + 8 * b, dst = tiles_s + b * kStageBytes;
