@@ -2,10 +2,10 @@
 // the GL_LINES vertex stream (xyz, relPos) that glDrawTransformFeedback consumes in the reference
 // (src/shaders/hair/02_tess_stream/*.glsl, draw call src/fx/hair.cc:141-173).
 //
-// One thread per SEGMENT (patch, k = 0..nsubsegments-1): it evaluates the three Hermite curves of the patch at both ends of
-// the segment once, then walks the (instance, isoline) pairs — whose only own work is the barycentric mix — and writes each
-// segment as one aligned 32-byte store (two float4). Consecutive threads own consecutive segments, so a warp writes
-// contiguous 512-byte runs, every output sector exactly once. The (instance, isoline) samples are hashed once per block into
+// One thread per curve POINT (patch, k = 0..nsubsegments): it evaluates the three Hermite curves of the patch there once, then
+// walks the (instance, isoline) pairs — whose only own work is the barycentric mix — takes the far end of its segment from
+// the next lane by shuffle and writes the segment as one aligned 32-byte store (two float4). Consecutive lanes own
+// consecutive segments, so a warp writes contiguous 512-byte runs, every output sector exactly once. The (instance, isoline) samples are hashed once per block into
 // shared memory. Write-bound: 32 B per segment out; 6 control points x 2 planes x 16 B per patch in, once per patch row.
 // (The first version ran one thread per POINT and instance: 12 control-point loads, the Hermite basis and the sample hash
 // per point — instruction-bound at 0.26 of the HBM write roofline, profiles/r01_stages.txt.)
@@ -15,6 +15,7 @@
 #include "hair_gen.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace bh {
 
@@ -86,7 +87,65 @@ __device__ __forceinline__ void store_segment(float4* dst, float4 a, float4 b) {
 
 constexpr int kTessSmemSamples = 2048;           // (instance, isoline) pairs cached per block; beyond that they are hashed in place
 
-__global__ void __launch_bounds__(256) tess_stream_kernel(const float4* __restrict__ pos, const float4* __restrict__ tan,
+__global__ void __launch_bounds__(256) tess_stream_points_kernel(const float4* __restrict__ pos, const float4* __restrict__ tan,
+                                                          const int* __restrict__ patch, long long npatches, int N, float scale,
+                                                          int ninstances, int nlines, int nsub, uint32_t seed,
+                                                          float4* __restrict__ out) {
+  __shared__ Sample smp[kTessSmemSamples];
+  const int ncurves = ninstances * nlines;
+  const bool cached = ncurves <= kTessSmemSamples;
+  if (cached) {
+    for (int i = threadIdx.x; i < ncurves; i += blockDim.x) smp[i] = tess_sample(i / nlines, i % nlines, nlines, seed);
+    __syncthreads();
+  }
+  // One thread per curve POINT; a warp covers 32 consecutive points of the (patch, k = 0..nsub) sequence and owns the 31
+  // segments between them (consecutive warps overlap by one point), so every point's Hermite evaluation happens once per
+  // warp and the far end of a segment arrives by shuffle. Pairs that straddle two patches are not segments and write nothing.
+  const int npts = nsub + 1;
+  const long long total = npatches * npts;
+  const long long nwarps_total = (total - 1 + 30) / 31;                       // warp w starts at point 31 * w
+  const long long line_stride = 2LL * nsub;                                   // float4 per (instance, patch, isoline)
+  const long long inst_stride = npatches * nlines * line_stride;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warp_step = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp0; w < nwarps_total; w += warp_step) {
+    const long long g = w * 31 + lane;
+    const bool live = g < total;
+    const long long gg = live ? g : total - 1;                                // clamp: every lane takes part in the shuffles
+    const int k = (int)(gg % npts);
+    const long long pa = gg / npts;
+    const int2* e2 = reinterpret_cast<const int2*>(patch + 6 * pa);           // 24-byte records: 8-byte aligned
+    const int2 ea = __ldg(e2), eb = __ldg(e2 + 1), ec = __ldg(e2 + 2);
+    const int e[6] = { ea.x, ea.y, eb.x, eb.y, ec.x, ec.y };
+    float4 P0[3], P1[3], T0[3], T1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      P0[c] = __ldg(pos + e[2 * c]); P1[c] = __ldg(pos + e[2 * c + 1]);
+      T0[c] = __ldg(tan + e[2 * c]); T1[c] = __ldg(tan + e[2 * c + 1]);
+      T0[c].x = __fmul_rn(T0[c].x, scale); T0[c].y = __fmul_rn(T0[c].y, scale); T0[c].z = __fmul_rn(T0[c].z, scale);   // tcs_stream_hair.glsl:41
+      T1[c].x = __fmul_rn(T1[c].x, scale); T1[c].y = __fmul_rn(T1[c].y, scale); T1[c].z = __fmul_rn(T1[c].z, scale);
+    }
+    const float rel0 = __fdiv_rn((float)(e[0] % N), (float)N);
+    const CurvePoint a = tess_point(k, nsub, N, rel0, P0, P1, T0, T1);
+    const float rel_next = __shfl_down_sync(0xffffffffu, a.rel, 1);
+    const bool writes = live && lane < 31 && k < nsub && g + 1 < total;       // this lane starts a segment whose end is in lane + 1
+    float4* dst_inst = out + pa * nlines * line_stride + 2 * k;               // (instance 0, isoline 0) of this patch
+    for (int inst = 0; inst < ninstances; ++inst, dst_inst += inst_stride) {
+      float4* dst = dst_inst;
+      for (int line = 0; line < nlines; ++line, dst += line_stride) {
+        const Sample sm = cached ? smp[inst * nlines + line] : tess_sample(inst, line, nlines, seed);
+        const float4 v = tess_mix(a, sm);
+        const float4 vn = make_float4(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1),
+                                      __shfl_down_sync(0xffffffffu, v.z, 1), rel_next);
+        if (writes) store_segment(dst, v, vn);
+      }
+    }
+  }
+}
+
+// Variant for many (instance, isoline) pairs per patch: one thread per SEGMENT evaluates both of its ends itself (twice the
+// Hermite work, no shuffles, no idle lanes at patch boundaries); ahead once the barycentric loop dominates.
+__global__ void __launch_bounds__(256) tess_stream_segments_kernel(const float4* __restrict__ pos, const float4* __restrict__ tan,
                                                           const int* __restrict__ patch, long long npatches, int N, float scale,
                                                           int ninstances, int nlines, int nsub, uint32_t seed,
                                                           float4* __restrict__ out) {
@@ -131,11 +190,23 @@ __global__ void __launch_bounds__(256) tess_stream_kernel(const float4* __restri
 
 cudaError_t launch_tess_stream(const float4* pos, const float4* tan, const int* patch, long long npatches, int nverts, float scale,
                                int ninstances, int nlines, int nsub, unsigned seed, float4* out, cudaStream_t stream) {
-  const long long total = npatches * nsub;                                     // one thread per (patch, segment)
-  if (total <= 0 || ninstances <= 0 || nlines <= 0) return cudaSuccess;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  tess_stream_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pos, tan, patch, npatches, nverts, scale, ninstances, nlines, nsub, seed, out);
+  if (npatches <= 0 || ninstances <= 0 || nlines <= 0) return cudaSuccess;
+  // measured on B200 (profiles/r01_stages.txt): the point kernel wins while the per-point Hermite evaluation dominates
+  // (0.91 vs 0.71 of the HBM write roofline at the reference's 3 x 2 pairs), the segment kernel once the pair loop does
+  // (1.03 vs 0.90 at 6 x 4)
+  static const int pairs_env = [] { const char* e = getenv("BH_TESS_POINT_KERNEL_MAX_PAIRS"); return e ? atoi(e) : -1; }();   // tuning knob
+  const int max_pairs = pairs_env >= 0 ? pairs_env : 7;                      // crossover measured at 8 pairs (0.86 vs 0.87)
+  if ((long long)ninstances * nlines <= max_pairs) {
+    const long long total = npatches * (nsub + 1);                             // one thread per curve point, 31 new points per warp
+    long long blocks = ((total + 30) / 31 * 32 + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    tess_stream_points_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pos, tan, patch, npatches, nverts, scale, ninstances, nlines, nsub, seed, out);
+  } else {
+    const long long total = npatches * nsub;                                   // one thread per (patch, segment)
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    tess_stream_segments_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pos, tan, patch, npatches, nverts, scale, ninstances, nlines, nsub, seed, out);
+  }
   return cudaGetLastError();
 }
 

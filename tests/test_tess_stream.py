@@ -47,7 +47,9 @@ def test_oracle_stream_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,ninst,nlines,nsub,rows,cols", [(4, 3, 2, 16, 6, 8), (16, 1, 1, 1, 5, 7), (32, 2, 5, 7, 8, 16), (8, 4, 3, 64, 4, 8)])
+@pytest.mark.parametrize("N,ninst,nlines,nsub,rows,cols", [(4, 3, 2, 16, 6, 8), (16, 1, 1, 1, 5, 7), (32, 2, 5, 7, 8, 16), (8, 4, 3, 64, 4, 8),
+                                                          # > 7 (instance, isoline) pairs: the thread-per-segment kernel; 31 / 33 points per patch: warp seams
+                                                          (8, 5, 3, 8, 4, 8), (16, 7, 4, 30, 6, 8), (4, 2, 2, 32, 16, 16), (16, 13, 1, 3, 5, 7)])
 def test_tess_stream_bit_exact_vs_oracle(N, ninst, nlines, nsub, rows, cols):
     S = rows * cols
     _, tri, pos, vel, tan, patch = scene(rows, cols, N, steps=3)

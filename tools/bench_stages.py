@@ -76,7 +76,7 @@ tri = bb.sphere_scalp_triangles(rows, cols)
 patches = bb.build_patch_indices(tri, N)
 sim.tess_set_patches(patches)
 npatch = patches.size // 6
-for (ni, nl, ns) in ((3, 2, 16), (1, 1, 4), (6, 4, 32)):
+for (ni, nl, ns) in ((3, 2, 16), (1, 1, 4), (4, 2, 16), (4, 3, 16), (4, 4, 16), (6, 4, 32)):
     count = sim.tess_stream(ni, nl, ns, 7, download=False)
     ms = timed(lambda: sim.tess_stream(ni, nl, ns, 7, download=False))
     report("tess_stream", f"{npatch} patches ({rows}x{cols} scalp, N = {N}), ninstances {ni}, nlines {nl}, nsubsegments {ns}: {count} float4 out",
