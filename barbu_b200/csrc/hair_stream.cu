@@ -1,4 +1,5 @@
-// hair_stream.cu — the streaming step kernel for sm_100a (the hot path at nverts % 8 == 0).
+// hair_stream.cu — the streaming step kernel for sm_100a (the hot path: nverts % 8 == 0 or the reference's nverts = 4,
+// 8 constraint iterations, sphere collider and up to 8 capsules).
 //
 // Same arithmetic as hair_step.cu (one dispatch of cs_simulation.glsl:170-208 + PingPongBuffer::swap,
 // written back in place), organised for Blackwell:
@@ -21,6 +22,12 @@
 //    .rn forms; in the exact profile a product is written fma(a, b, -0.0) with the -0.0 taken from a
 //    kernel parameter, because ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even with
 //    explicit rounding modifiers and --fmad=false.
+//  * The instruction cache decides what may be inlined: the hot loop (two chunk bodies x two input variants + their
+//    push-out blocks) is ~2,000 instructions against an L1.5 I-cache of 32 KB, so every rare path — the IEEE fallback of
+//    the inverse square root, the exact capsule chain — is ONE out-of-line call, and the capsule variant runs a single
+//    chunk body.
+//  * Tile order alternates between consecutive launches (StepArgs::reverse, set by bh_step): a launch starts where the
+//    previous one ended, in the part of the state that is still in L2.
 //
 // Algorithmic traffic: 16 B pos + 16 B vel read and the same written = 64 B per vertex per launch.
 #include "hair_step.cuh"
