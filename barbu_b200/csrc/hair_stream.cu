@@ -319,11 +319,11 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     dp[q] = PM::dot(vd[q], vd[q], nz);
   }
   bool ok = true;
-  if (PM::kRangeChecked) {                                                  // all eight operands inside the branch-free range?
-    unsigned key = 0u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) key = max(key, max(M::range_key(lo(dp[q])), M::range_key(hi(dp[q]))));
-    ok = key < M::kRangeKeyEnd;
+  if (PM::kRangeChecked) {
+    // All eight operands inside the branch-free range? fmin/fmax skip NaN operands, and a NaN is no reason to leave the
+    // branch-free sequence (it returns NaN like the builtins): a strand that went NaN — the reference's arithmetic makes
+    // some, normalize(0) — must not drag its warp through the IEEE path at every step for the rest of the run.
+    ok = !(min8(dp) < M::kFastLo) && !(max8(dp) >= __int_as_float(0x7f800000));
   }
   neg_inversesqrt_batch<PM>(dp, ninv, ok, nz);
 #pragma unroll
