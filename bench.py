@@ -50,7 +50,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock, throttle reasons and power sampled during the timed region (B200_PROFILING.md): NVML, else nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
@@ -64,7 +64,48 @@ class ClockSampler:
     def mark_end(self):
         self.t_end = time.time()
 
+    def _nvml_loop(self, pynvml, handle):
+        names = [("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap)]
+        smax = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                pw = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                self.rows.append((time.time(), [str(sm), str(smax)] + ["Active" if mask & bit else "Not Active" for _, bit in names] + [str(pw)]))
+            except pynvml.NVMLError:
+                pass
+            self._stop.wait(0.002)
+
     def start(self):
+        # NVML in-process (a sample every ~2 ms: the timed region of a short run still gets tens of samples); nvidia-smi as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            handle = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        handle = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, "encode") else cand); break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self._stop = threading.Event()
+            self.proc = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True,
@@ -80,11 +121,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self._stop.set()
+            self._thread.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         def num(x):
             try:
                 return float(x)
