@@ -25,6 +25,7 @@ struct StepArgs {
   int use_drag;
   int ncaps;
   int reverse;            // streaming kernel: hand the tiles out from the last one down (see bh_step: alternates per launch)
+  int tip_step;           // streaming kernel: step of a root chunk at which the tip of the previous strand leaves the pipeline
   Capsule caps[kMaxCapsules];
   // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
   // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.

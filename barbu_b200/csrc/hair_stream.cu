@@ -338,7 +338,10 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     if (q == 3) {
       const V3 dF = vsub<M>(hi3(D[3]), hi3(in[3]));                         // s_particles[i].velocity = p1_bis - p1 (cs:116)
       V3 fw = M::scale(dF, a.damp);                                         // cs:119-121
-      if (root_in_stage<RS>(j, 7)) fw = s.heldd;                            // the tip (a root follows it) keeps its own d
+      // the tip keeps its own d. nverts % 8 == 0: a root follows it (step 7 of the root chunk); otherwise the slots after it
+      // in its last chunk are out of bounds for the tensor map — TMA fills them with NaN on the way in and drops them on the
+      // way out — and the tip leaves at step (nverts % 8) - 1 of the next root chunk (tip_step, set by the launcher)
+      if (RS == 8 ? j == a.tip_step : root_in_stage<RS>(j, 7)) fw = s.heldd;
       s.heldd = dF;
       if (SEP && !recompute && s.heldHit) fw = M::reflect(fw, s.heldN);     // cs:137, with the normal found one step ago
       if (recompute) {                                                      // sphere + capsules again from D(i, 8), now with the velocity
@@ -461,7 +464,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   const uint32_t tiles_s = base + warp * kWarpTileBytes;
   const uint32_t bar_s = base + kWarps * (kWarpTileBytes + kRingBytes) + warp * 16;
 
-  const int chunks = NS == 8 ? a.nverts / kK : 1;                           // per row
+  const int chunks = NS == 8 ? (a.nverts + kK - 1) / kK : 1;                // per row; the last one may be ragged (see tip_step)
   const long long nrows = NS == 8 ? a.nstrands : a.nstrands / 2;
   const unsigned int ntiles = (unsigned int)((nrows + 31) / 32);
 
@@ -594,8 +597,11 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
   const int promo = promo_env >= 0 ? promo_env : (nverts >= 64 ? 256 : 128);
   const CUtensorMapL2promotion l2 = promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
                                     promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  // Out-of-bounds elements (the slots after the tip when nverts % 8 != 0, the rows after the last strand of a ragged tile)
+  // arrive as NaN: NaN vertices run through the branch-free arithmetic at full speed, touch no collider and are never
+  // stored, whereas zeros would be degenerate segments (length 0) and send the warp through the IEEE fallback.
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
 struct DeviceInfo { int sms = 0; bool ready[12] = {}; int blocks_per_sm[12] = {}; };
@@ -617,6 +623,7 @@ void fill_capsule_bounds(StepArgs& b) {
 template <class PM, bool ORIGIN, int NS, bool CAPS = false>
 cudaError_t launch_stream_t(const StepArgs& a_in, cudaStream_t stream, unsigned int* tile_counter, int variant) {
   StepArgs a = a_in;
+  a.tip_step = a.nverts % kK == 0 ? kK - 1 : a.nverts % kK - 1;
   if (CAPS) fill_capsule_bounds(a);
   static DeviceInfo info[64];
   static std::mutex mu;
@@ -703,9 +710,11 @@ cudaError_t selftest_inversesqrt(unsigned long long* mismatches) {
 
 bool stream_kernel_eligible(const StepArgs& a) {
   static const bool disabled = [] { const char* e = getenv("BH_NO_STREAM_KERNEL"); return e && e[0] == '1'; }();
-  // nverts % 8 == 0, or the reference's own nverts = 4 (two strands per tensor row: an even number of strands; the
-  // launcher gives the last strand of an odd count to the per-strand kernel)
-  const bool shape_ok = (a.nverts >= kK && a.nverts % kK == 0) || (a.nverts == 4 && a.nstrands >= 2);
+  // any nverts >= 2 (a ragged last chunk is handled by the tensor map's bounds, see make_plane_map); the reference's own
+  // nverts = 4 packs two strands per tensor row (an even number of strands: the launcher gives the last strand of an odd
+  // count to the per-strand kernel)
+  static const bool ragged_ok = [] { const char* e = getenv("BH_NO_RAGGED_STREAM"); return !(e && e[0] == '1'); }();
+  const bool shape_ok = a.nverts == 4 ? a.nstrands >= 2 : (a.nverts >= 2 && (ragged_ok || a.nverts % kK == 0));
   return !disabled && a.iterations == kK && a.ncaps >= 0 && a.ncaps <= kMaxCapsules && shape_ok &&
          a.nstrands <= 0x7fffffffLL && a.r2 <= 1.8446744073709551616e19f && encode_tiled() != nullptr;
 }

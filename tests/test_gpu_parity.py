@@ -72,6 +72,29 @@ def test_step_bit_exact_ragged_shapes(S, N):
     assert_bit_equal(gv, rv, "velocities")
 
 
+@pytest.mark.parametrize("N", [2, 3, 5, 6, 7, 9, 12, 15, 17, 20, 31, 33, 47, 100, 127])
+@pytest.mark.parametrize("S,sphere", [(1000, SPHERE), (4099, (0.1, -0.05, 0.2, 1.05))])
+def test_stream_kernel_any_vertex_count_bit_exact(S, N, sphere):
+    """Vertices per strand that are not a multiple of 8 stay on the streaming kernel: the last chunk of a strand is ragged,
+    the tensor map fills its out-of-bounds slots with NaN and drops them on the way out, and the tip leaves the pipeline at
+    step (N % 8) - 1 of the next root chunk. Many steps, contacts from the first one (the second sphere reaches past the
+    roots), a ragged last tile."""
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(10):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.45, sphere=sphere)
+        assert sim.kernel_kind == 0
+        sim.upload(pos, vel)
+        for _ in range(10):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+
+
 @pytest.mark.parametrize("N,scale", [(16, 1.45), (32, 1.45), (32, 1.0)])
 def test_config1_size_many_steps_bit_exact(N, scale):
     """BASELINE config 1 shape (4,096 strands) over 60 steps from the cold state, contacts included."""
