@@ -218,8 +218,9 @@ __device__ __forceinline__ float max8(const u64 (&v)[4]) {
 
 // One step of the stream pipeline: slot j of the current chunk. Returns whether any lane was pushed out of the
 // collider (warp-uniform), i.e. whether the next step must be the SEP variant.
-//   RS   : root stride of this chunk. 0: no root in it (an inner chunk of a strand); 8: vertex 0 of a strand is in slot 0
-//          (nverts % 8 == 0), so at step j stage j holds a root and step 7 finalises the tip of the previous strand;
+//   RS   : root stride of this chunk. 0: no root in it (an inner chunk of a strand); 8: vertex 0 of a strand is in slot 0,
+//          so at step j stage j holds a root, and step a.tip_step finalises the tip of the previous strand (step 7 when
+//          nverts % 8 == 0; earlier when the previous strand's last chunk was ragged, its empty slots being NaN);
 //          4: the chunk holds two whole strands of the reference's own nverts = 4 (interop.h:8), roots in slots 0 and 4.
 //          Stage k holds at step j the vertex of slot j - k (mod 8; negative: of the previous chunk).
 //   SEP  : the previous step had a push-out; inputs come from s.P.
@@ -234,7 +235,7 @@ __device__ __forceinline__ bool root_in_stage(const int j, const int stage) {
 //          arithmetic (scalar, hair_collide.cuh). The vertex leaving the pipeline then recomputes its whole collision
 //          chain with its final velocity one step later, so no collision normals are carried.
 // The exact capsule arithmetic runs for few warps and must not bloat the step body (the instruction cache holds the hot
-// loop only if the rare paths stay out of line): one out-of-line copy each, called per vertex.
+// loop only if the rare paths stay out of line): one out-of-line copy each, one call per step.
 struct Pos8 { V3p c[4]; };                       // the eight positions of a step: pair q = stages q (lo) and q + 4 (hi)
 template <class M> __device__ __noinline__ Pos8 caps_slow(const StepArgs& a, Pos8 x, const unsigned skip) {
 #pragma unroll 1
