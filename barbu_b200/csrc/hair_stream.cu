@@ -543,8 +543,10 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     float4* bV = bP + kPlaneTile / 16;
     const bool root_chunk = !live || cC == 0;
     if (NS == 4) stream_chunk<PM, ORIGIN, 4, CAPS>(a, nz, s, sep, 0x11u, bP, bV, myR, sw);
-    // capsule variant: one step body for both kinds of chunk (its extra tests already crowd the instruction cache)
-    else if (CAPS) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw, root_chunk ? 0 : 8);
+    // capsule variant, exact profile: one step body for both kinds of chunk (its extra tests already crowd the instruction
+    // cache: with two bodies the "arms" scene of tests/reports/config3.py runs at 6.7 ms per launch instead of 5.1); the
+    // fast profile's bodies are small enough to keep both (far capsules 2.25 -> 1.91 ms, "arms" 4.29 -> 3.97 ms)
+    else if (CAPS && PM::kRangeChecked) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw, root_chunk ? 0 : 8);
     else if (root_chunk) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     else stream_chunk<PM, ORIGIN, 0, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     prev_root_chunk = root_chunk;
