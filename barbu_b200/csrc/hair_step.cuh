@@ -30,6 +30,9 @@ struct StepArgs {
   // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
   // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.
   float capb[kMaxCapsules][4];
+  // ... and a capsule-shaped second bound for the warps the first one lets through: axis (b - a), 1 / |b - a|^2 (0 for a
+  // degenerate capsule) and the squared radius with its margin, for a packed fast-arithmetic distance to the axis.
+  float capt[kMaxCapsules][8];   // abx, aby, abz, inv_l2, r2_tight, 0, 0, 0
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.

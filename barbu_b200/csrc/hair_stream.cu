@@ -270,6 +270,31 @@ __device__ __forceinline__ bool caps_may_touch(const StepArgs& a, const V3p (&X)
   return touch;
 }
 
+// Second, capsule-shaped bound for a warp the bounding spheres let through: squared distance to the capsule's axis in fast
+// packed arithmetic against the radius with a margin (fill_capsule_bounds). Still conservative — it only decides whether
+// the exact chain is entered — but it fits the capsule, not a sphere around it.
+__device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&X)[4]) {
+  bool touch = false;
+#pragma unroll 1
+  for (int k = 0; k < a.ncaps; ++k) {
+    const Capsule& c = a.caps[k];
+    const V3p A = { pk(c.ax, c.ax), pk(c.ay, c.ay), pk(c.az, c.az) };
+    const V3p AB = { pk(a.capt[k][0], a.capt[k][0]), pk(a.capt[k][1], a.capt[k][1]), pk(a.capt[k][2], a.capt[k][2]) };
+    const float inv_l2 = a.capt[k][3];
+    u64 dd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const V3p ap = sub3(X[q], A);
+      const u64 d = fma2(ap.z, AB.z, fma2(ap.y, AB.y, mul2_contractable(ap.x, AB.x)));
+      const u64 nt = pk(-__saturatef(lo(d) * inv_l2), -__saturatef(hi(d) * inv_l2));   // -clamp(t, 0, 1); NaN -> 0
+      const V3p e = { fma2(nt, AB.x, ap.x), fma2(nt, AB.y, ap.y), fma2(nt, AB.z, ap.z) };
+      dd[q] = fma2(e.z, e.z, fma2(e.y, e.y, mul2_contractable(e.x, e.x)));
+    }
+    touch = touch || (min8(dd) < a.capt[k][4]);
+  }
+  return touch;
+}
+
 template <class PM, bool ORIGIN, int RS, bool SEP, bool CAPS>
 __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pipe& s, const int j, const bool fin_root,
                                             float4* slotP, float4* slotV, float* slotR) {
@@ -413,7 +438,8 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #pragma unroll
   for (int q = 0; q < 4; ++q) C[q] = D[q];
   if (any_hit) sphere_push_out(); else s.heldHit = false;
-  const bool any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
+  bool any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
+  if (any_cap) any_cap = __any_sync(0xffffffffu, caps_tight_touch(a, C));     // rare: only behind the bounding spheres
   if (any_cap) {
     // every vertex in flight that is not a root (cs:149-151: index > 0); the vertex in stage 7 is skipped, the next step
     // recomputes its whole chain (sphere included) together with its velocity
@@ -620,6 +646,18 @@ void fill_capsule_bounds(StepArgs& b) {
     b.capb[k][0] = (float)(c.ax + hx); b.capb[k][1] = (float)(c.ay + hy); b.capb[k][2] = (float)(c.az + hz);
     b.capb[k][3] = std::nextafter((float)(R * R), INFINITY);
     if (!(b.capb[k][3] == b.capb[k][3])) b.capb[k][3] = INFINITY;            // NaN capsule: always take the exact path
+    // capsule-shaped bound: radius widened by 1e-3 relative plus 1e-5 of the coordinate magnitudes involved
+    const float abx = c.bx - c.ax, aby = c.by - c.ay, abz = c.bz - c.az;
+    const float l2 = abx * abx + aby * aby + abz * abz;
+    const double mag = 1.0 + std::fmax(std::fmax(std::fabs((double)c.ax), std::fabs((double)c.ay)), std::fabs((double)c.az)) +
+                       std::fmax(std::fmax(std::fabs((double)c.bx), std::fabs((double)c.by)), std::fabs((double)c.bz));
+    const double Rt = std::fabs((double)c.r) * (1.0 + 1e-3) + 1e-5 * mag;
+    b.capt[k][0] = abx; b.capt[k][1] = aby; b.capt[k][2] = abz;
+    b.capt[k][3] = l2 > 0.0f ? 1.0f / l2 : 0.0f;
+    b.capt[k][4] = std::nextafter((float)(Rt * Rt), INFINITY);
+    if (!(b.capt[k][4] == b.capt[k][4]) || !(b.capt[k][3] == b.capt[k][3]) || std::isinf(b.capt[k][3])) {   // NaN / overflowing capsule
+      b.capt[k][0] = b.capt[k][1] = b.capt[k][2] = b.capt[k][3] = 0.0f; b.capt[k][4] = INFINITY;
+    }
   }
 }
 
