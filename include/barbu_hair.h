@@ -125,8 +125,8 @@ int  bh_host_alloc(void** ptr, uint64_t nbytes);     /* cudaMallocHost */
 int  bh_host_free(void* ptr);
 /* Kernel launches issued by this sim so far (bench.py's gpu_launches claim). */
 int64_t bh_launch_count(const bh_sim* sim);
-/* Which step kernel the current shape/parameters select: 0 streaming (TMA tiles + packed fp32x2; nverts % 8 == 0,
- * 8 iterations, no capsules), 1 per-strand pipelined (any nverts), 2 generic (any iteration count). */
+/* Which step kernel the current shape/parameters select: 0 streaming (TMA tiles + packed fp32x2; any nverts >= 2,
+ * 8 iterations, sphere + capsules), 1 per-strand pipelined (nverts = 1, corner cases), 2 generic (any iteration count). */
 int  bh_step_kernel_kind(const bh_sim* sim);
 /* Exhaustive device check of the exact profile's branch-free 1/sqrt(x) (scalar and packed fp32x2 forms) against
  * the IEEE-754 builtins over every finite binary32 >= 2^-102. *mismatches must come back 0. */
