@@ -258,8 +258,8 @@ def test_sphere_scalp_generation_bit_exact_and_sharded(rows, cols, N):
     assert_bit_equal(bb.build_patch_indices(tri, N), po.patch_indices(tri, N), "patch indices")
 
 
-def test_step_host_equals_device_resident_step():
-    S, N = 20000, 16
+@pytest.mark.parametrize("S,N", [(20000, 16), (70001, 20), (33333, 4)])     # several slices; ragged chunks; odd strand count at N = 4
+def test_step_host_equals_device_resident_step(S, N):
     pos, vel = ragged_state(S, N)
     gp, gv = gpu_steps(pos, vel, S, N, 1, DT, substeps=4, scale=1.0, sphere=SPHERE)
     hp, hv = bb.PinnedBuffer(4 * S * N), bb.PinnedBuffer(4 * S * N)
@@ -434,7 +434,8 @@ CAPSULE_SETS = {
 
 @pytest.mark.parametrize("caps", sorted(CAPSULE_SETS))
 @pytest.mark.parametrize("S,N,sphere", [(600, 16, SPHERE), (4100, 32, SPHERE), (1001, 8, (0.05, 0.1, -0.02, 0.9)),
-                                        (2050, 4, (0.0, 0.0, 0.0, 1.02)), (333, 64, SPHERE)])
+                                        (2050, 4, (0.0, 0.0, 0.0, 1.02)), (333, 64, SPHERE),
+                                        (1500, 12, SPHERE), (777, 21, (0.05, 0.1, -0.02, 0.9)), (900, 5, SPHERE)])   # ragged last chunk
 def test_stream_kernel_capsules_bit_exact(caps, S, N, sphere):
     """Capsule colliders (extension, oracle-defined) through the streaming kernel: conservative bounding test, exact
     capsule chain for the warps that may touch, collision chain of the leaving vertex recomputed with its velocity."""
