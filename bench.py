@@ -56,6 +56,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.other_mask = 0                        # every NVML clocks-event bit seen while sampling (NVML path only)
         self.t_begin = self.t_end = None
 
     def mark_begin(self):
@@ -74,6 +75,7 @@ class ClockSampler:
                 mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
                 pw = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
                 self.rows.append((time.time(), [str(sm), str(smax)] + ["Active" if mask & bit else "Not Active" for _, bit in names] + [str(pw)]))
+                self.other_mask |= mask
             except pynvml.NVMLError:
                 pass
             self._stop.wait(0.002)
@@ -145,8 +147,22 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower() == "active" for r in inside)]
         sm = [num(r[0]) for r in inside]
         pw = [num(r[6]) for r in inside if num(r[6]) is not None]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(num(r[1]) for r in inside) if inside else None,
-                "reasons": reasons, "samples": len(sm), "window": window, "power_w_max": max(pw) if pw else None}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(num(r[1]) for r in inside) if inside else None,
+               "reasons": reasons, "samples": len(sm), "window": window, "power_w_max": max(pw) if pw else None}
+        if self.proc == "nvml":
+            # for the reader who sees a median below the maximum with an empty `reasons`: every event bit NVML reported at any
+            # sample of this sampler's life (pre-roll included), by name
+            try:
+                import pynvml
+                bits = {"gpu_idle": pynvml.nvmlClocksEventReasonGpuIdle, "applications_clocks_setting": pynvml.nvmlClocksEventReasonApplicationsClocksSetting,
+                        "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap, "hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                        "sync_boost": pynvml.nvmlClocksEventReasonSyncBoost, "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                        "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_power_brake_slowdown": pynvml.nvmlClocksEventReasonHwPowerBrakeSlowdown,
+                        "display_clock_setting": pynvml.nvmlClocksEventReasonDisplayClockSetting}
+                out["event_bits_seen"] = sorted(k for k, b in bits.items() if self.other_mask & b)
+            except Exception:
+                pass
+        return out
 
 
 _emit_fd = None
