@@ -655,7 +655,7 @@ void fill_capsule_bounds(StepArgs& b) {
     b.capt[k][0] = abx; b.capt[k][1] = aby; b.capt[k][2] = abz;
     b.capt[k][3] = l2 > 0.0f ? 1.0f / l2 : 0.0f;
     b.capt[k][4] = std::nextafter((float)(Rt * Rt), INFINITY);
-    if (!(b.capt[k][4] == b.capt[k][4]) || !(b.capt[k][3] == b.capt[k][3]) || std::isinf(b.capt[k][3])) {   // NaN / overflowing capsule
+    if (!std::isfinite(b.capt[k][4]) || !std::isfinite(b.capt[k][3]) || !std::isfinite(l2)) {   // NaN / overflowing capsule: no second bound
       b.capt[k][0] = b.capt[k][1] = b.capt[k][2] = b.capt[k][3] = 0.0f; b.capt[k][4] = INFINITY;
     }
   }
