@@ -426,6 +426,10 @@ CAPSULE_SETS = {
     # overlapping capsules + a degenerate one (a == b: a sphere) + one far away that is never touched
     "overlap": [((0.0, 1.0, 0.0), (0.3, 1.4, 0.2), 0.25), ((0.1, 1.1, 0.1), (0.1, 1.1, 0.1), 0.3),
                 ((0.2, 1.2, 0.0), (-0.4, 1.3, 0.1), 0.2), ((50.0, 0.0, 0.0), (51.0, 0.0, 0.0), 0.5)],
+    # parameters that defeat the conservative bounds (they must then step aside, not decide): an axis whose squared length
+    # overflows, a capsule far from the origin, a zero radius, a NaN end point
+    "extreme": [((-1.0e20, 0.3, 0.0), (1.0e20, 0.3, 0.0), 0.4), ((1.0e6, 0.0, 0.0), (1.0e6, 1.0, 0.0), 0.5),
+                ((0.2, 0.9, 0.1), (0.4, 1.2, 0.1), 0.0), ((float("nan"), 0.0, 0.0), (0.0, 1.0, 0.0), 0.3)],
     # eight capsules (the maximum) in a ring below the scalp, where the strands hang
     "ring8": [((float(np.cos(k * np.pi / 4)), -1.1, float(np.sin(k * np.pi / 4))),
                (float(np.cos((k + 1) * np.pi / 4)), -1.25, float(np.sin((k + 1) * np.pi / 4))), 0.12) for k in range(8)],
@@ -455,7 +459,7 @@ def test_stream_kernel_capsules_bit_exact(caps, S, N, sphere):
         gp, gv, _ = sim.download()
     assert_bit_equal(gp, rp, "positions")
     assert_bit_equal(gv, rv, "velocities")
-    if caps != "ring8" or N >= 16:
+    if caps not in ("ring8", "extreme") or (caps == "ring8" and N >= 16):
         # the case must exercise the capsule push-out: some non-root vertex sits on a capsule surface
         x = rp[:, :3].astype(np.float64).reshape(S, N, 3)[:, 1:].reshape(-1, 3)
         on = np.zeros(len(x), bool)
