@@ -37,7 +37,7 @@ class Hair {
   // process state there and a run-time value here.
   struct Parameters_t {
     struct { float maxlength = 0.50f; } sim;                                  // hair.h:29
-    struct { int ninstances = 3; int nlines = 2; int nsubsegments = 16; } tess;   // hair.h:33-35 (render side; kept for the caller)
+    struct { int ninstances = 3; int nlines = 2; int nsubsegments = 16; } tess;   // hair.h:33-35 (used by stream())
     struct { float lengthScale = 1.450f; } render;                            // hair.h:41 -> uScaleFactor (hair.cc:108)
     struct { int nroots = 0; int nControlPoints = 0; } readonly;              // hair.h:45-48
     struct {
@@ -63,6 +63,7 @@ class Hair {
   /* Release all allocated resources (hair.cc:66-87). */
   void deinit() {
     if (sim_) { bh_destroy(sim_); sim_ = nullptr; }
+    patches_uploaded_ = false;
     nroots_ = 0;
     patch_indices_.clear();
   }
@@ -140,6 +141,27 @@ class Hair {
   /* Copy path: planes to host memory (NULL = skip), V float4 each. */
   bool download(float* pos4, float* vel4, float* tan4) { return sim_ && check(bh_download(sim_, pos4, vel4, tan4), "bh_download"); }
 
+  /* The tess-stream half of Hair::render (hair.cc:141-173): the interpolated render strands as the GL_LINES vertex stream
+   * (xyz, relPos; two float4 per sub-segment) that the reference captures by transform feedback and draws with
+   * glDrawTransformFeedback, for params().tess. Returns the number of float4 (0 on failure); they stay on the device
+   * (bh_tess_device_buffer) and are also copied to `out4_host` when it is not null (room for stream_count() float4). */
+  std::int64_t stream_count() {
+    if (!ensure_patches()) return 0;
+    const bh_tess_params t = tess_params();
+    const std::int64_t n = bh_tess_stream_count(sim_, &t);
+    return n > 0 ? n : 0;
+  }
+  std::int64_t stream(float* out4_host = nullptr) {
+    if (!ensure_patches()) return 0;
+    const bh_tess_params t = tess_params();
+    if (!check(bh_tess_stream(sim_, &t, out4_host), "bh_tess_stream")) return 0;
+    return stream_count();
+  }
+
+  /* Strand state to / from a BARBUHS1 file (the reference has no persistence; include/barbu_hair.h describes the format). */
+  bool save_state(const char* path) { return sim_ && check(bh_save_state(sim_, path, nullptr), "bh_save_state"); }
+  bool load_state(const char* path) { return sim_ && check(bh_load_state(sim_, path, nullptr), "bh_load_state"); }
+
   bh_sim* handle() noexcept { return sim_; }
 
  private:
@@ -152,6 +174,21 @@ class Hair {
     // hair.h:99 is uninitialised); here the shader default (0,0,0,1) (cs_simulation.glsl:43) stands until one is set.
     if (has_sphere_) for (int i = 0; i < 4; ++i) p.sphere[i] = boundingsphere_[i];
     return check(bh_set_params(sim_, &p), "bh_set_params");
+  }
+  bool ensure_patches() {                                                        // the element buffer of init_mesh, on the device
+    if (!initialized()) { log_debug("Hair::stream called before setup()."); return false; }   // like render(), hair.cc:128-131
+    if (patch_indices_.empty()) { log_error("Hair::stream: the scalp had no faces."); return false; }
+    if (!patches_uploaded_) {
+      if (!check(bh_tess_set_patches(sim_, patch_indices_.data(), static_cast<std::int64_t>(patch_indices_.size())), "bh_tess_set_patches")) return false;
+      patches_uploaded_ = true;
+    }
+    return true;
+  }
+  bh_tess_params tess_params() const noexcept {
+    bh_tess_params t;
+    t.ninstances = params_.tess.ninstances; t.nlines = params_.tess.nlines; t.nsubsegments = params_.tess.nsubsegments;
+    t.seed = params_.b200.seed;
+    return t;
   }
   static bool check(int rc, const char* what) {
     if (rc == BH_OK) return true;
@@ -173,6 +210,7 @@ class Hair {
   float boundingsphere_[4] = { 0.f, 0.f, 0.f, 1.f };
   bool has_sphere_ = false;
   std::vector<std::int32_t> patch_indices_;
+  bool patches_uploaded_ = false;
 };
 
 }  // namespace barbu

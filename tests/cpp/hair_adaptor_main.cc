@@ -3,10 +3,13 @@
 // Usage: hair_adaptor_main <in.bin> <out.bin>
 //   in : int64 S, int64 F, int32 N, int32 nframes, uint32 seed, float dt, float scale, float sphere[4], int32 math,
 //        float pos[S*3], float nrm[S*3], int32 tri[F*3]
-//   out: int64 V, int64 nelems, float pos4[V*4], float vel4[V*4], float tan4[V*4], int32 patch[nelems]
+//   out: int64 V, int64 nelems, float pos4[V*4], float vel4[V*4], float tan4[V*4], int32 patch[nelems],
+//        int64 nstream, float stream4[nstream*4]   (tess-stream of the final state, default tessellation; a save_state /
+//        load_state round trip is made in between and must not change it)
 // Exit codes: 0 ok, 2 usage/io, 3 module not initialised after setup.
 #include <cstdint>
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "../../include/barbu_hair.hpp"
@@ -49,11 +52,21 @@ int main(int argc, char** argv) {
   std::vector<float> p4(4 * V), v4(4 * V), t4(4 * V);
   if (!hair.download(p4.data(), v4.data(), t4.data())) return 3;
   const std::int64_t nelems = static_cast<std::int64_t>(hair.patch_indices().size());
+  // the render-side half: tess-stream, then state file round trip, then the stream again — identical
+  std::vector<float> stream4(4 * static_cast<size_t>(hair.stream_count())), stream4b(stream4.size());
+  const std::int64_t nstream = hair.stream(stream4.data());
+  {
+    const std::string state = std::string(argv[2]) + ".state";
+    if (!hair.save_state(state.c_str()) || !hair.load_state(state.c_str())) return 3;
+    std::remove(state.c_str());
+    if (hair.stream(stream4b.data()) != nstream || stream4 != stream4b) return 3;
+  }
   f = std::fopen(argv[2], "wb");
   if (!f) return 2;
   std::fwrite(&V, 8, 1, f); std::fwrite(&nelems, 8, 1, f);
   std::fwrite(p4.data(), 4, p4.size(), f); std::fwrite(v4.data(), 4, v4.size(), f); std::fwrite(t4.data(), 4, t4.size(), f);
   std::fwrite(hair.patch_indices().data(), 4, hair.patch_indices().size(), f);
+  std::fwrite(&nstream, 8, 1, f); std::fwrite(stream4.data(), 4, 4 * static_cast<size_t>(nstream), f);
   std::fclose(f);
   std::printf("hair_adaptor_main: %lld strands x %d control points, %d frames, tangent plane at byte %llu, %lld patch elements\n",
               (long long)S, N, nframes, (unsigned long long)hair.tangent_plane_offset(), (long long)nelems);

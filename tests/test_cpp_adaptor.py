@@ -33,7 +33,10 @@ def run_driver(root_pos, root_nrm, tri, N, nframes, seed, dt, scale, sphere, mat
         planes.append(np.frombuffer(raw, np.float32, 4 * V, off).reshape(V, 4).copy())
         off += 16 * V
     patch = np.frombuffer(raw, np.int32, nelems, off).copy()
-    return res, (planes[0], planes[1], planes[2], patch)
+    off += 4 * nelems
+    (nstream,) = struct.unpack_from("<q", raw, off)
+    stream = np.frombuffer(raw, np.float32, 4 * nstream, off + 8).reshape(nstream, 4).copy()
+    return res, (planes[0], planes[1], planes[2], patch, stream)
 
 
 def test_adaptor_driver_builds_and_fails_loudly_without_a_device():
@@ -56,7 +59,7 @@ def test_adaptor_matches_oracle_bit_exact(N, scale, nframes):
     S = rows * cols
     res, out = run_driver(root_pos, root_nrm, tri, N, nframes, 1234, float(DT), scale, SPHERE)
     assert res.returncode == 0, res.stderr
-    gp, gv, gt, patch = out
+    gp, gv, gt, patch, stream = out
     par = po.default_params(dt=float(DT), scale=scale, sphere=SPHERE)
     for _ in range(nframes):
         po.step(pos, vel, S, N, par)
@@ -64,3 +67,5 @@ def test_adaptor_matches_oracle_bit_exact(N, scale, nframes):
     assert_bit_equal(gv, vel, "velocities")
     assert_bit_equal(gt, po.init_tangents(root_nrm, N), "tangent plane")
     assert_bit_equal(patch, po.patch_indices(tri, N), "patch indices")
+    # Hair::stream() = the tess-stream half of the reference's render(), default tessellation 3 x 2 x 16, seed = params.b200.seed
+    assert_bit_equal(stream, po.tess_stream(pos, gt, patch, N, scale, 3, 2, 16, 1234), "tess-stream")
