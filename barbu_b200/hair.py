@@ -444,8 +444,8 @@ class Hair:
 
     init()/deinit(), setup(scalp), update(dt), set_bounding_sphere(vec4), initialized() behave as in
     src/fx/hair.cc:26-125: `setup` with an unusable scalp logs and leaves the module uninitialised,
-    `update` before `setup` is a silent no-op. `render` stays with the reference's GL path, which
-    reads plane 0 / plane 2 of buffer 0 (hair.cc:371-389).
+    `update` before `setup` is a silent no-op. `stream()` is the tess-stream half of `render` (hair.cc:141-173);
+    the draw itself stays with the reference's GL path, which reads plane 0 / plane 2 of buffer 0 (hair.cc:371-389).
     """
 
     @dataclass
@@ -456,6 +456,9 @@ class Hair:
         seed: int = 1234                 # stands in for srand(time(NULL)), app.cc:96-97
         substeps: int = 1                # extension: 1 == reference
         math: int = BH_MATH_EXACT
+        ninstances: int = 3              # tess.ninstances, hair.h:33
+        nlines: int = 2                  # tess.nlines, hair.h:34
+        nsubsegments: int = 16           # tess.nsubsegments, hair.h:35
 
     def __init__(self, device: int = 0, params: Optional["Hair.Parameters"] = None):
         self.params = params or Hair.Parameters()
@@ -464,6 +467,7 @@ class Hair:
         self.sim: Optional[HairSim] = None
         self.patch_indices: Optional[np.ndarray] = None
         self._sphere = None
+        self._patches_uploaded = False
         self.log = []
 
     def init(self):
@@ -472,7 +476,7 @@ class Hair:
     def deinit(self):
         if self.sim is not None:
             self.sim.close()
-        self.sim, self.nroots, self.patch_indices = None, 0, None
+        self.sim, self.nroots, self.patch_indices, self._patches_uploaded = None, 0, None, False
 
     def initialized(self) -> bool:
         return self.nroots != 0
@@ -514,3 +518,17 @@ class Hair:
             return
         self.sim.configure(scale=self.params.length_scale)                   # uniform re-sent every frame, hair.cc:108
         self.sim.step(dt, self.params.substeps)
+
+    def stream(self, download: bool = True):
+        """The tess-stream half of Hair::render (hair.cc:141-173) for the tess parameters (hair.h:33-35): the GL_LINES
+        vertex stream (count, 4) of the interpolated render strands, or its length when `download` is False."""
+        if not self.initialized():
+            self.log.append("Calling Hair::render without initialization.")  # hair.cc:128-131
+            return None
+        if self.patch_indices is None:
+            self.log.append("The scalp has no faces: nothing to tessellate.")
+            return None
+        if not self._patches_uploaded:
+            self.sim.tess_set_patches(self.patch_indices)
+            self._patches_uploaded = True
+        return self.sim.tess_stream(self.params.ninstances, self.params.nlines, self.params.nsubsegments, self.params.seed, download)

@@ -321,8 +321,10 @@ def test_hair_module_mirror():
     assert_bit_equal(gp, pos)
     assert_bit_equal(gv, vel)
     assert_bit_equal(gt2, gt, "tangent plane untouched by the simulation")
+    # the tess-stream half of render(), default tessellation (hair.h:33-35)
+    assert_bit_equal(hair.stream(), po.tess_stream(pos, gt, hair.patch_indices, N, 1.45, 3, 2, 16, 1234), "tess-stream")
     hair.deinit()
-    assert not hair.initialized()
+    assert not hair.initialized() and hair.stream() is None
 
 
 # ---- streaming kernel (TMA tiles, persistent warps, packed fp32x2) ---------------------------------
