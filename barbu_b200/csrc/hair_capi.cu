@@ -431,8 +431,12 @@ int bh_selftest_math(int device, uint64_t* mismatches) {
 
 int bh_set_skin(bh_sim* s, const float* rest_root_pos3, const int32_t* joints4, const float* weights3) {
   if (!s || !rest_root_pos3 || !joints4 || !weights3) return fail(BH_ERR_INVALID, "bh_set_skin: NULL argument");
-  DeviceGuard g(s->device);
   const size_t S = (size_t)s->nstrands;
+  // the kernel reads dq + 8 * joint: remember the range so that bh_skin_roots can refuse a palette that is too short
+  int32_t jmin = 0, jmax = 0;
+  for (size_t q = 0; q < 4 * S; ++q) { if (joints4[q] < jmin) jmin = joints4[q]; if (joints4[q] > jmax) jmax = joints4[q]; }
+  if (jmin < 0) return fail(BH_ERR_INVALID, "bh_set_skin: negative joint index");
+  DeviceGuard g(s->device);
   if (!s->skin_rest3) BH_CUDA(cudaMalloc(&s->skin_rest3, sizeof(float) * 3 * S));
   if (!s->skin_joints4) BH_CUDA(cudaMalloc(&s->skin_joints4, sizeof(int) * 4 * S));
   if (!s->skin_weights3) BH_CUDA(cudaMalloc(&s->skin_weights3, sizeof(float) * 3 * S));
@@ -440,6 +444,7 @@ int bh_set_skin(bh_sim* s, const float* rest_root_pos3, const int32_t* joints4, 
   BH_CUDA(cudaMemcpyAsync(s->skin_joints4, joints4, sizeof(int) * 4 * S, cudaMemcpyHostToDevice, s->stream));
   BH_CUDA(cudaMemcpyAsync(s->skin_weights3, weights3, sizeof(float) * 3 * S, cudaMemcpyHostToDevice, s->stream));
   BH_CUDA(cudaStreamSynchronize(s->stream));
+  s->skin_max_joint = jmax;
   return BH_OK;
 }
 
@@ -447,6 +452,7 @@ int bh_skin_roots(bh_sim* s, const float* dq_palette, int njoints) {
   if (!s || !dq_palette || njoints <= 0) return fail(BH_ERR_INVALID, "bh_skin_roots: bad argument");
   if (!s->skin_rest3) return fail(BH_ERR_NOT_INITIALIZED, "bh_skin_roots: call bh_set_skin first");
   if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_skin_roots: no strand state");
+  if (s->skin_max_joint >= njoints) return fail(BH_ERR_INVALID, "bh_skin_roots: a joint index of bh_set_skin is outside the palette (njoints too small)");
   DeviceGuard g(s->device);
   if (njoints > s->skin_dq_cap) {
     cudaFree(s->skin_dq); s->skin_dq = nullptr; s->skin_dq_cap = 0;

@@ -76,6 +76,7 @@ __device__ __forceinline__ void cross3(const float a[3], const float b[3], float
   o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(b[2], a[0]));
   o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(b[0], a[1]));
 }
+// vec4 * mat3x4, one column: left to right (glm/detail/type_mat3x4.inl:454-464)
 __device__ __forceinline__ float dot4(const float* a, const float* b) {
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2])), __fmul_rn(a[3], b[3]));
 }
@@ -106,7 +107,9 @@ __global__ void __launch_bounds__(256) skin_roots_dq_kernel(const float* __restr
         B[c] = __fadd_rn(__fadd_rn(__fmul_rn(q[0][4 + c], w[0]), __fmul_rn(q[1][4 + c], w[1])),
                          __fadd_rn(__fmul_rn(q[2][4 + c], w[2]), __fmul_rn(q[3][4 + c], w[3])));
       }
-      const float inv = __frcp_rn(__fsqrt_rn(dot4(A, A)));
+      // glm::dot(vec4, vec4) pairs the products: (x*x + y*y) + (z*z + w*w)   (glm/detail/func_geometric.inl:58-65)
+      const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[0], A[0]), __fmul_rn(A[1], A[1])),
+                                                       __fadd_rn(__fmul_rn(A[2], A[2]), __fmul_rn(A[3], A[3])))));
 #pragma unroll
       for (int c = 0; c < 4; ++c) { A[c] = __fmul_rn(A[c], inv); B[c] = __fmul_rn(B[c], inv); }
       float c1[3], c2[3], cab[3];

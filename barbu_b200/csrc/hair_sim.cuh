@@ -58,6 +58,7 @@ struct bh_sim {
   float* skin_weights3 = nullptr;
   float* skin_dq = nullptr;
   int skin_dq_cap = 0;
+  int skin_max_joint = 0;                // largest joint index bh_set_skin stored (bh_skin_roots checks njoints against it)
   // tess-stream stage
   int* tess_patch = nullptr;            // device copy of the patch element buffer
   int64_t tess_npatches = 0;

@@ -27,7 +27,8 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 }
 __device__ __forceinline__ float u01(uint32_t h) { return __fmul_rn((float)(h >> 8), 1.0f / 16777216.0f); }
 __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fadd_rn(__fmul_rn(a2, b2), __fmul_rn(a3, b3)));
+  // vec4 * mat4, one column: the four products summed left to right (third_party/glm/glm/detail/type_mat4x4.inl:584-595)
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2)), __fmul_rn(a3, b3));
 }
 
 struct Sample { float x, y, z; };

@@ -133,7 +133,8 @@ int  bh_step_kernel_kind(const bh_sim* sim);
 int  bh_selftest_math(int device, uint64_t* mismatches);
 
 /* ---- extension: dual-quaternion skinned roots (formula of shared/inc_skinning.glsl:22-31,54-82) */
-/* Stores rest roots + skin data once; bh_skin_roots rewrites vertex 0 of every strand in plane 0. */
+/* Stores rest roots + skin data once; bh_skin_roots rewrites vertex 0 of every strand in plane 0. Joint indices are
+ * validated: negative ones are refused by bh_set_skin, ones >= njoints by bh_skin_roots (BH_ERR_INVALID). */
 int  bh_set_skin(bh_sim* sim, const float* rest_root_pos3, const int32_t* joints4, const float* weights3);
 int  bh_skin_roots(bh_sim* sim, const float* dq_palette, int njoints);
 

@@ -322,7 +322,8 @@ void bho_sphere_scalp(int R, int C, float* pos3, float* nrm3, int32_t* tri) {
  * Formula of src/shaders/shared/inc_skinning.glsl: apply_skinning (l.22-31): early-out when
  * weights.x <= 1e-6, w.w = 1 - (x+y+z); skinning_DQBS (l.54-82): antipodality fix
  * weights.xyz *= sign(dot(q[3], q[k])) (sign(0) = 0), A = Ma*w, B = Mb*w in GLM mat4*vec4 order
- * (m0*x + m1*y) + (m2*z + m3*w), normalise by inversesqrt(dot(A,A)), rotate + translate.
+ * (m0*x + m1*y) + (m2*z + m3*w), normalise by inversesqrt(dot(A,A)), rotate + translate. Pinned bit for bit against
+ * the shader source compiled over the reference's GLM (oracle/_ref, tests/test_oracle_vs_reference_live.py).
  * dq palette: njoints * 8 floats (real xyzw, dual xyzw), as uSkinningDatas texels 2j, 2j+1. */
 static inline void cross3(const float a[3], const float b[3], float o[3]) {
   o[0] = a[1] * b[2] - b[1] * a[2];   /* glm::cross: x.y*y.z - y.y*x.z, ... */
@@ -359,7 +360,8 @@ void bho_skin_roots_dq(const float* rest_pos3, const float* rest_nrm3, const int
         A[c] = (q[0][c] * w[0] + q[1][c] * w[1]) + (q[2][c] * w[2] + q[3][c] * w[3]);
         B[c] = (q[0][4 + c] * w[0] + q[1][4 + c] * w[1]) + (q[2][4 + c] * w[2] + q[3][4 + c] * w[3]);
       }
-      const float inv = 1.0f / sqrtf(((A[0] * A[0] + A[1] * A[1]) + A[2] * A[2]) + A[3] * A[3]);
+      /* glm::dot(vec4, vec4) = (x*x + y*y) + (z*z + w*w)  (glm/detail/func_geometric.inl:58-65) */
+      const float inv = 1.0f / sqrtf((A[0] * A[0] + A[1] * A[1]) + (A[2] * A[2] + A[3] * A[3]));
       for (int c = 0; c < 4; ++c) { A[c] = A[c] * inv; B[c] = B[c] * inv; }
       dq_rotate(A, v);
       float cab[3];
@@ -391,8 +393,9 @@ uint64_t bho_fnv1a64(const void* data, uint64_t n) {
  * Defined here because the reference leaves it to the implementation (no reference parity is claimed for them):
  *   - isoline tess coordinates: x = k / nsubsegments (k = 0..nsubsegments), y = line / nlines (equal_spacing ideal);
  *   - primitive order: instance-major, then patch, line, segment;
- *   - vector arithmetic order as GLM evaluates the same expressions (dot4 = (x*x' + y*y') + (z*z' + w*w'),
- *     vec * mat = per-column dot, mat3x4 * vec3 = (m0*v.x + m1*v.y) + m2*v.z);
+ *   - vector arithmetic order: as the reference's vendored GLM evaluates the same expressions — vec4 * mat4 = per column
+ *     ((x*x' + y*y') + z*z') + w*w', mat3x4 * vec3 = (m0*v.x + m1*v.y) + m2*v.z — pinned bit for bit by
+ *     tests/test_oracle_vs_reference_live.py against the shader stages compiled over GLM (oracle/_ref);
  *   - the random pair: the reference indexes a std430 `vec3[]` view of 4096 mt19937(random_device) floats with
  *     int(y*40 + instance) % 4096 (tes:52-54), reading out of bounds past element 1023 (SURVEY §8 a-ext). Kept: the index
  *     formula; replaced: the table, by the counter-based hash below (seeded, reproducible, no out-of-bounds). */
@@ -405,7 +408,8 @@ void bho_tess_random_pair(uint32_t seed, int index, float st[2]) {
   st[0] = u01(lowbias32(seed + 0x9E3779B9u * (uint32_t)(2 * index + 1)));
   st[1] = u01(lowbias32(seed + 0x9E3779B9u * (uint32_t)(2 * index + 2)));
 }
-static inline float dot4(const float a[4], const float b[4]) { return (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]); }
+/* vec4 * mat4, one column: GLM sums the four products left to right (glm/detail/type_mat4x4.inl:584-595) */
+static inline float dot4(const float a[4], const float b[4]) { return ((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3]; }
 /* hermite_mix: vU * mHermit * B, xyz only (w = h0 + h1 is dropped by the TES) */
 static void hermite3(const float p0[3], const float p1[3], const float t0[3], const float t1[3], float u, float out[3]) {
   static const float M[4][4] = { { 2.0f, -3.0f, 0.0f, 1.0f }, { -2.0f, 3.0f, 0.0f, 0.0f }, { 1.0f, -2.0f, 1.0f, 0.0f }, { 1.0f, -1.0f, 0.0f, 0.0f } };

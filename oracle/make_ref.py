@@ -29,6 +29,16 @@ What it produces
                                the same lexical edits plus: `#include`/include guards, `precision`, `layout(...) in;`
                                and the image declaration removed (the harness provides imageStore), and the one
                                swizzle assignment `roots.xyz = e;` spelled component-wise.
+  _ref/tess_skin.gen.inc       the stages either side of the simulation, same lexical edits:
+                               shared/inc_constants.glsl; from shared/inc_maths.glsl the functions sample_triangle2
+                               (l.107-115), hermite_mix (210-228), maprange (239-241), smoothstep2 (263-266); from
+                               shared/inc_skinning.glsl apply_skinning (22-31), get_dual_quaternions_matrices (37-52) and
+                               skinning_DQBS (54-82) — `out`/`inout` parameters become references, the subroutine uniform
+                               `uSkinning` is bound to skinning_DQBS by the harness, the one swizzle assignment
+                               `_weights.xyz *= e;` is spelled component-wise; and the `main` bodies of the four
+                               02_tess_stream stages (vs/tcs/tes/gs -> vs_main/tcs_main/tes_main/gs_main, one namespace
+                               each) with their interface declarations (layout(...) lines) removed — the harness
+                               declares the stage inputs and outputs.
   _ref/hair_init_simulation.gen.inc   body of Hair::init_simulation, src/fx/hair.cc:236-328
                                       (up to, not including, the GL buffer creation).
   _ref/hair_init_mesh.gen.inc         element loop of Hair::init_mesh, src/fx/hair.cc:397-409.
@@ -100,6 +110,53 @@ def gen_marschner():
     open(os.path.join(OUT, "marschner.gen.inc"), "w").write(out)
 
 
+def extract_function(text, name):
+    """The definition of GLSL function `name` (return type line to the closing brace in column 0)."""
+    m = re.findall(r"^(?:vec[234]|float|void) " + name + r"\([^)]*\) \{\n.*?\n\}\n", text, flags=re.M | re.S)
+    assert len(m) == 1, f"expected one definition of {name}, found {len(m)}"
+    return m[0]
+
+
+def glsl_fn_to_cpp(src):
+    """glsl_to_cpp plus what function parameters and the skinning source need."""
+    src = re.sub(r"\b(?:inout|out)\s+(\w+)\s+", r"\1& ", src)
+    src = re.sub(r"\bin\s+(uvec4|mat4)\b", r"\1", src)
+    src = re.sub(r"(\w+)\.xyz\s*\*=\s*([^;]*);", r"{ const vec3 t_ = \2; \1.x *= t_.x; \1.y *= t_.y; \1.z *= t_.z; }", src)
+    src = re.sub(r"\.xyzw\b(?!\()", ".xyzw()", src)
+    return glsl_to_cpp(src)
+
+
+def stage_main(path, name):
+    """`void main() {...}` of one tess-stream stage, renamed; everything else in those files is interface declaration."""
+    src = open(path).read()
+    m = re.findall(r"^void main\(\) \{\n.*?\n\}\n", src, flags=re.M | re.S)
+    assert len(m) == 1, f"{path}: expected one main()"
+    body = re.sub(r"^#if 1\s*$", "#if 1", m[0], flags=re.M)
+    return glsl_fn_to_cpp(body).replace("void main()", f"void {name}()")
+
+
+def gen_tess_skin():
+    sh = os.path.join(REF, "src/shaders")
+    maths = open(os.path.join(sh, "shared/inc_maths.glsl")).read()
+    skin = open(os.path.join(sh, "shared/inc_skinning.glsl")).read()
+    parts = ["namespace shared_inc {"]
+    parts.append(glsl_to_cpp(open(os.path.join(sh, "shared/inc_constants.glsl")).read()))
+    for fn in ("sample_triangle2", "hermite_mix", "maprange", "smoothstep2"):
+        parts.append(glsl_fn_to_cpp(extract_function(maths, fn)))
+    parts.append("void skinning_DQBS(uvec4 _indices, vec4 _weights, vec3& v, vec3& n);")
+    for fn in ("apply_skinning", "get_dual_quaternions_matrices", "skinning_DQBS"):
+        parts.append(glsl_fn_to_cpp(extract_function(skin, fn)))
+    parts.append("}  // namespace shared_inc")
+    ts = os.path.join(sh, "hair/02_tess_stream")
+    for stage in ("vs", "tcs", "tes", "gs"):
+        parts.append(f"namespace stage_{stage} {{\nusing namespace shared_inc;\nSTAGE_{stage.upper()}_INTERFACE")
+        parts.append(stage_main(os.path.join(ts, f"{stage}_stream_hair.glsl"), f"{stage}_main"))
+        parts.append(f"}}  // namespace stage_{stage}")
+    out = "\n".join(parts)
+    assert "layout(" not in out and "#include" not in out and "subroutine" not in out
+    open(os.path.join(OUT, "tess_skin.gen.inc"), "w").write(out)
+
+
 def slice_lines(path, first, last):
     lines = open(os.path.join(REF, path)).read().split("\n")
     return "\n".join(lines[first - 1:last]) + "\n"
@@ -122,4 +179,5 @@ if __name__ == "__main__":
     gen_shader()
     gen_host()
     gen_marschner()
+    gen_tess_skin()
     print("generated into", OUT)

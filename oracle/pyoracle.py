@@ -196,6 +196,50 @@ def tess_stream(pos4, tan4, patch, nverts: int, scale: float, ninstances: int, n
     return out
 
 
+def tess_random_table(seed: int, size: int = 4096) -> np.ndarray:
+    """(size, 2) float32: the oracle's seeded pair for every index of the reference's random table (HAIR_TF_RANDOMBUFFER_SIZE)."""
+    out = np.empty((size, 2), np.float32)
+    st = np.zeros(2, np.float32)
+    for i in range(size):
+        oracle().bho_tess_random_pair(C.c_uint32(seed), C.c_int(i), _p(st))
+        out[i] = st
+    return out
+
+
+def ref_tess_skin_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libbarbu_ref_tess_skin.so"))
+
+
+def _ref_tess_skin() -> C.CDLL:
+    if "tess_skin" not in _ref_cache:
+        _ref_cache["tess_skin"] = C.CDLL(os.path.join(REF_DIR, "libbarbu_ref_tess_skin.so"))
+    return _ref_cache["tess_skin"]
+
+
+def ref_tess_stream(pos4, tan4, patch, nverts: int, scale: float, ninstances: int, nlines: int, nsubsegments: int, randtable):
+    """The reference's four tess-stream shader stages (SOURCE compiled over GLM, oracle/_ref) on the CPU; `randtable` is the
+    content of the random buffer, (4096, 2) float32."""
+    patch = np.ascontiguousarray(patch, np.int32)
+    npatches = patch.size // 6
+    out = np.empty((npatches * ninstances * nlines * nsubsegments * 2, 4), np.float32)
+    randtable = np.ascontiguousarray(randtable, np.float32)
+    assert randtable.shape == (4096, 2)
+    _ref_tess_skin().ref_tess_stream(_p(np.ascontiguousarray(pos4, np.float32)), _p(np.ascontiguousarray(tan4, np.float32)), _p(patch),
+                                     C.c_int64(npatches), C.c_int(nverts), C.c_float(scale), C.c_int(ninstances), C.c_int(nlines),
+                                     C.c_int(nsubsegments), _p(randtable), _p(out))
+    return out
+
+
+def ref_skin_dq(rest_pos3, rest_nrm3, joints4, weights3, dq):
+    """apply_skinning + skinning_DQBS of the reference's inc_skinning.glsl (SOURCE compiled over GLM, oracle/_ref)."""
+    S = rest_pos3.shape[0]
+    op, on = np.empty((S, 3), np.float32), np.empty((S, 3), np.float32)
+    _ref_tess_skin().ref_skin_dq(_p(np.ascontiguousarray(rest_pos3, np.float32)), _p(np.ascontiguousarray(rest_nrm3, np.float32)),
+                                 _p(np.ascontiguousarray(joints4, np.int32)), _p(np.ascontiguousarray(weights3, np.float32)),
+                                 _p(np.ascontiguousarray(dq, np.float32)), C.c_int64(S), _p(op), _p(on))
+    return op, on
+
+
 # ---- scalp input ----------------------------------------------------------------------------------
 
 def obj_scalp(path: str):

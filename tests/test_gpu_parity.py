@@ -205,6 +205,43 @@ def test_dq_skinned_roots_bit_exact():
     assert_bit_equal(gp, expect, "skinned roots")
 
 
+def test_dq_skinned_roots_bit_exact_vs_reference_fixture():
+    """skin_roots_dq_kernel against tests/golden/tess_skin.npz: positions the REFERENCE's apply_skinning + skinning_DQBS
+    (inc_skinning.glsl over GLM, tests/golden/make_tess_skin_golden.py) produced — antipodal joints, Epsilon() early-out."""
+    t = golden("tess_skin")
+    S, N = t["skin_pos"].shape[0], 4
+    pos = np.zeros((S * N, 4), np.float32); pos[:, 3] = 0.125
+    pos[::N, :3] = t["skin_pos"]
+    with bb.HairSim(S, N) as sim:
+        sim.upload(pos, np.zeros_like(pos))
+        sim.set_skin(t["skin_pos"], t["skin_joints"], t["skin_weights"])
+        sim.skin_roots(t["skin_dq"])
+        gp, _, _ = sim.download()
+    expect = pos.copy()
+    expect[::N, :3] = t["skin_out_pos"]
+    assert_bit_equal(gp, expect, "skinned roots vs the reference shader")
+
+
+def test_skin_roots_rejects_joint_indices_outside_the_palette():
+    """A joint index the palette does not hold must be refused (BH_ERR_INVALID), not read out of bounds on the device."""
+    S, N = 64, 4
+    pos = np.zeros((S * N, 4), np.float32)
+    root = np.zeros((S, 3), np.float32)
+    w = np.full((S, 3), 0.25, np.float32)
+    dq = np.zeros((6, 8), np.float32); dq[:, 3] = 1.0
+    with bb.HairSim(S, N) as sim:
+        sim.upload(pos, pos.copy())
+        j = np.zeros((S, 4), np.int32); j[17, 2] = 6
+        sim.set_skin(root, j, w)
+        with pytest.raises(bb.BarbuHairError):
+            sim.skin_roots(dq)                                             # 6 joints: index 6 is out of range
+        sim.skin_roots(np.concatenate([dq, dq[:1]]))                       # 7 joints: fine
+        j[17, 2] = -1
+        with pytest.raises(bb.BarbuHairError):
+            sim.set_skin(root, j, w)                                       # negative index
+        sim.step(float(DT), 1)                                             # the context is still healthy
+
+
 # ---- fast profile: tolerance ----------------------------------------------------------------------
 
 @pytest.mark.parametrize("N", [16, 32])
@@ -228,11 +265,62 @@ def test_fast_profile_within_1e5_after_one_step(N):
     po.step(rp, rv, S, N, par, nthreads=8)
     gp, gv = gpu_steps(wp, wv, S, N, 1, scale=1.45, sphere=SPHERE, math=bb.BH_MATH_FAST)
     err = rel_err(gp, rp)
-    # contact bifurcations (a vertex within rounding of the sphere surface) are excluded by quantile, and reported
-    assert np.quantile(err, 0.999) <= TOL, f"p99.9 {np.quantile(err, 0.999):.3e} max {err.max():.3e}"
+    # the MAXIMUM over all vertices, not a quantile. The only vertices that may be set aside are those of a strand in
+    # grazing contact — some vertex at or before them lies within 4 ulp of the collider surface in the exact result, where
+    # a different rounding legitimately flips `dp < r*r` — and they are listed, and there may be at most two such strands.
+    excluded = contact_bifurcations(err > TOL, rp, S, N, SPHERE)
+    assert err[~excluded].max() <= TOL and excluded.reshape(S, N).any(axis=1).sum() <= 2, \
+        f"max {err.max():.3e}; set aside (grazing contact): {np.nonzero(excluded)[0].tolist()}"
     # velocities are cancellation differences: absolute tolerance scaled by segment length (App. B iv)
     seg = 1.45 * np.maximum(rp[:, 3], 1e-3)
-    assert np.quantile(np.abs(gv[:, :3] - rv[:, :3]).max(axis=1) / seg, 0.999) <= 1e-4
+    verr = np.abs(gv[:, :3] - rv[:, :3]).max(axis=1) / seg
+    assert verr[~excluded].max() <= 1e-4, f"velocity max {verr.max():.3e}"
+
+
+def contact_bifurcations(over, exact_pos, S, N, sphere, ulps=4):
+    """Mask of the vertices flagged in `over` that sit on a strand with a grazing contact at or before them: a vertex of the
+    exact result within `ulps` ulp of the sphere surface. Flagged vertices without such a contact stay un-excused."""
+    c, r = np.asarray(sphere[:3], np.float64), float(sphere[3])
+    dist = np.linalg.norm(exact_pos[:, :3].astype(np.float64) - c, axis=1).reshape(S, N)
+    grazing = np.abs(dist - r) <= ulps * float(np.spacing(np.float32(r)))
+    grazing[:, 0] = False                                                 # roots do not collide (cs:149-151)
+    upstream = np.cumsum(grazing, axis=1) > 0
+    return (over.reshape(S, N) & upstream).reshape(-1)
+
+
+def test_full_size_fast_profile_one_step_max_error():
+    """north_star's tolerance at configs[1]'s full size (2^20 strands x 32): from a settled state (30 frames of the exact
+    profile, which the tests above hold bit-identical to the oracle), ONE step of the fast profile against ONE step of the
+    exact profile over ALL 33,554,432 vertices: max relative error <= 1e-5 (grazing-contact strands listed, at most 0.002 %),
+    and 2,048 sampled strands of the exact side replayed by the CPU oracle, bit for bit."""
+    rows, cols, N = 1024, 1024, 32
+    S = rows * cols
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.45, sphere=SPHERE, math=bb.BH_MATH_EXACT)
+        sim.init_sphere_scalp(rows, cols, 0, bb.random_values(1234, 0, S))
+        for _ in range(30):
+            sim.step(float(DT), 1)
+        wp, wv, _ = sim.download()
+        sim.step(float(DT), 1)
+        ep, ev, _ = sim.download()
+        sim.upload(wp, wv)
+        sim.configure(math=bb.BH_MATH_FAST)
+        sim.step(float(DT), 1)
+        fp, fv, _ = sim.download()
+    finite = np.isfinite(ep[:, :3]).all(axis=1) & np.isfinite(wp[:, :3]).all(axis=1)   # strands the reference arithmetic itself turned into NaN (normalize(0), App. A note 2)
+    assert (~finite).reshape(S, N).any(axis=1).sum() <= S * 1e-4
+    assert np.array_equal(np.isfinite(fp[:, :3]).all(axis=1), np.isfinite(ep[:, :3]).all(axis=1)), "fast and exact disagree on which vertices are finite"
+    err = np.where(finite, rel_err(fp, ep), 0.0)
+    excluded = contact_bifurcations(err > 1e-5, ep, S, N, SPHERE)
+    nstr = int(excluded.reshape(S, N).any(axis=1).sum())
+    assert err[~excluded].max() <= 1e-5 and nstr <= 20, f"max {err.max():.3e}; {nstr} grazing-contact strands set aside: {np.nonzero(excluded.reshape(S, N).any(axis=1))[0][:40].tolist()}"
+    assert np.median(err) <= 1e-7 and np.quantile(err, 0.999) <= 2e-6, f"median {np.median(err):.3e} p99.9 {np.quantile(err, 0.999):.3e}"
+    idx = np.unique(np.concatenate([np.arange(0, S, 521), np.nonzero(excluded.reshape(S, N).any(axis=1))[0][:64]]))[:2048 + 64]
+    p, v = _sample_strands(wp, wv, S, N, idx)
+    po.step(p, v, idx.size, N, po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE), nthreads=16)
+    gp, gv = _sample_strands(ep, ev, S, N, idx)
+    assert_bit_equal(gp, p, "exact profile, sampled strands vs the oracle")
+    assert_bit_equal(gv, v, "exact profile, sampled velocities vs the oracle")
 
 
 # ---- generators, host path, API behaviour ---------------------------------------------------------

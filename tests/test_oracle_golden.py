@@ -59,3 +59,21 @@ def test_simplex_matches_glm():
     o = po.oracle()
     val = np.array([o.bho_simplex2(float(x), float(y)) for x, y in g["pts"]], np.float32)
     assert_bit_equal(val, g["val"], "glm::simplex(vec2)")
+
+
+@pytest.mark.parametrize("name", ["hair_N4_s145", "hair_N16_s100"])
+def test_tess_stream_matches_reference_shader_stages(name):
+    """tests/golden/tess_skin.npz: the reference's vs/tcs/tes/gs_stream_hair.glsl + inc_maths.glsl run over GLM (oracle/_ref)."""
+    g, t = golden(name), golden("tess_skin")
+    ninst, nlines, nsub, seed = (int(x) for x in t[f"tess_{name}_args"])
+    npatch = t[f"tess_{name}"].shape[0] // (ninst * nlines * nsub * 2)
+    got = po.tess_stream(g["pos10"], g["tan0"], g["patch"][:6 * npatch], int(g["nverts"]), float(t[f"tess_{name}_scale"]), ninst, nlines, nsub, seed)
+    assert_bit_equal(got, t[f"tess_{name}"], "tess-stream vertices")
+
+
+def test_dq_skinning_matches_reference_shader():
+    """tests/golden/tess_skin.npz: apply_skinning + skinning_DQBS of inc_skinning.glsl run over GLM (oracle/_ref)."""
+    t = golden("tess_skin")
+    p, n = po.skin_roots_dq(t["skin_pos"], t["skin_nrm"], t["skin_joints"], t["skin_weights"], t["skin_dq"])
+    assert_bit_equal(p, t["skin_out_pos"], "skinned positions")
+    assert_bit_equal(n, t["skin_out_nrm"], "skinned normals")

@@ -102,3 +102,92 @@ def test_simplex_noise_bit_exact_vs_glm_live():
     for x, y in (rng.standard_normal((500, 2)) * 37.0).astype(np.float32):
         a, b = np.float32(o.bho_simplex2(float(x), float(y))), np.float32(po.ref_simplex2(float(x), float(y)))
         assert a.view(np.uint32) == b.view(np.uint32), (x, y, a, b)
+
+
+# ---- the stages either side of the simulation, pinned the same way ---------------------
+
+@pytest.mark.parametrize("N,ninst,nlines,nsub", [(4, 3, 2, 16), (2, 1, 1, 1), (16, 2, 5, 7), (32, 4, 3, 9), (8, 45, 2, 3)])
+@pytest.mark.parametrize("seed", [0, 7])
+def test_tess_stream_bit_exact_vs_reference_shader_stages(N, ninst, nlines, nsub, seed):
+    """bho_tess_stream against the reference's vs/tcs/tes/gs_stream_hair.glsl + inc_maths.glsl (hermite_mix,
+    sample_triangle2, maprange, smoothstep2) run live over GLM, on random control points, tangents and patch lists. The
+    random table handed to the reference stages holds the oracle's seeded pairs; the index expression is the reference's."""
+    if not po.ref_tess_skin_available():
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(31 * N + seed)
+    S = 24
+    pos = np.zeros((S * N, 4), np.float32); tan = np.zeros((S * N, 4), np.float32)
+    pos[:, :3] = (rng.standard_normal((S * N, 3)) * [1.0, 30.0][seed % 2]).astype(np.float32)
+    pos[:, 3] = rng.random(S * N).astype(np.float32)
+    tan[:, :3] = (rng.standard_normal((S * N, 3)) * 0.3).astype(np.float32)
+    tri = rng.integers(0, S, (17, 3)).astype(np.int32)
+    patch = po.patch_indices(tri, N)
+    scale = [1.45, 0.37][seed % 2]
+    table = po.tess_random_table(1234 + seed)
+    got = po.tess_stream(pos, tan, patch, N, scale, ninst, nlines, nsub, 1234 + seed)
+    want = po.ref_tess_stream(pos, tan, patch, N, scale, ninst, nlines, nsub, table)
+    assert_bit_equal(got, want, "tess-stream vertices (xyz, relPos)")
+
+
+def test_tess_stream_special_values_bit_exact_vs_reference_shader_stages():
+    """Pairs on and across the fold of sample_triangle2 (s + t == 1, > 1 with s < t and s > t: the reference's overwrite of
+    st.x before st.y reads it), -0.0 / huge / NaN control points."""
+    if not po.ref_tess_skin_available():
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    N, S = 4, 8
+    rng = np.random.default_rng(3)
+    pos = np.zeros((S * N, 4), np.float32); tan = np.zeros((S * N, 4), np.float32)
+    pos[:, :3] = rng.standard_normal((S * N, 3)).astype(np.float32)
+    tan[:, :3] = rng.standard_normal((S * N, 3)).astype(np.float32)
+    pos[1, :3] = -0.0; pos[6, :3] = 3.0e37; pos[9, 0] = np.nan; tan[13, :3] = np.inf
+    tri = np.array([[0, 1, 2], [3, 4, 5], [5, 6, 7], [2, 2, 2]], np.int32)
+    patch = po.patch_indices(tri, N)
+    for seed in range(40):                                               # many tables: both sides of the fold for every (line, instance)
+        table = po.tess_random_table(seed)
+        want = po.ref_tess_stream(pos, tan, patch, N, 1.45, 3, 4, 5, table)
+        assert_bit_equal(po.tess_stream(pos, tan, patch, N, 1.45, 3, 4, 5, seed), want, f"seed {seed}")
+    s = po.tess_random_table(0)
+    assert ((s.sum(axis=1) > 1) & (s[:, 0] < s[:, 1])).any() and ((s.sum(axis=1) > 1) & (s[:, 0] > s[:, 1])).any()
+
+
+def random_dq_palette(rng, njoints, flip_some=True):
+    """Unit dual quaternions (real xyzw, dual xyzw) of random rigid transforms; some negated (q and -q are one rotation):
+    the antipodality fix of skinning_DQBS must see both signs."""
+    q = rng.standard_normal((njoints, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t = rng.standard_normal((njoints, 3)) * 0.5
+    x, y, z, w = q.T
+    dual = 0.5 * np.stack([t[:, 0] * w + t[:, 1] * z - t[:, 2] * y, -t[:, 0] * z + t[:, 1] * w + t[:, 2] * x,
+                           t[:, 0] * y - t[:, 1] * x + t[:, 2] * w, -t[:, 0] * x - t[:, 1] * y - t[:, 2] * z], axis=1)
+    dq = np.concatenate([q, dual], axis=1)
+    if flip_some:
+        dq[rng.random(njoints) < 0.5] *= -1.0
+    return dq.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_dq_skinning_bit_exact_vs_reference_shader(seed):
+    """bho_skin_roots_dq against apply_skinning + skinning_DQBS of the reference's inc_skinning.glsl run live over GLM:
+    random palettes with antipodal joints, weights at and below the Epsilon() early-out, zero and negative weights,
+    repeated joints, orthogonal real parts (sign(0) = 0)."""
+    if not po.ref_tess_skin_available():
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(500 + seed)
+    S, J = 400, 13
+    dq = random_dq_palette(rng, J)
+    if seed == 3:                                                        # exactly orthogonal real parts: dot == 0 -> sign 0
+        dq[0, :4] = (1, 0, 0, 0); dq[1, :4] = (0, 1, 0, 0); dq[2, :4] = (0, 0, 0, 1)
+    pos = (rng.standard_normal((S, 3)) * 2.0).astype(np.float32)
+    nrm = rng.standard_normal((S, 3)).astype(np.float32)
+    joints = rng.integers(0, J, (S, 4)).astype(np.int32)
+    if seed == 3:
+        joints[:50] = rng.integers(0, 3, (50, 4))
+    w = rng.dirichlet([1.0, 1.0, 1.0, 1.0], S)[:, :3].astype(np.float32)
+    w[0] = (0.0, 0.5, 0.5); w[1] = (1e-6, 0.5, 0.4); w[2] = (np.float32(1e-6) + np.float32(1e-12), 0.3, 0.3)
+    w[3] = (1.0000001e-6, 0.0, 0.0); w[4] = (1.0, 0.0, 0.0); w[5] = (0.7, 0.7, 0.7); w[6] = (0.5, -0.25, 0.5)
+    w[7] = (-0.5, 0.5, 0.5); w[8] = (np.nan, 0.5, 0.5)
+    joints[9] = (4, 4, 4, 4)
+    gp, gn = po.skin_roots_dq(pos, nrm, joints, w, dq)
+    rp, rn = po.ref_skin_dq(pos, nrm, joints, w, dq)
+    assert_bit_equal(gp, rp, "skinned positions")
+    assert_bit_equal(gn, rn, "skinned normals")
+    assert np.array_equal(gp[0], pos[0]) and np.array_equal(gp[1], pos[1])      # weights.x <= Epsilon(): untouched

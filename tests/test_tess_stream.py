@@ -67,6 +67,24 @@ def test_tess_stream_bit_exact_vs_oracle(N, ninst, nlines, nsub, rows, cols):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hair_N4_s145", "hair_N16_s100"])
+def test_tess_stream_bit_exact_vs_reference_fixture(name):
+    """The CUDA kernel against tests/golden/tess_skin.npz — vertices the REFERENCE's four tess-stream shader stages and
+    inc_maths.glsl produced when run over GLM (tests/golden/make_tess_skin_golden.py), no oracle in between."""
+    from tests.util import golden
+    g, t = golden(name), golden("tess_skin")
+    ninst, nlines, nsub, seed = (int(x) for x in t[f"tess_{name}_args"])
+    N, S = int(g["nverts"]), g["root_pos"].shape[0]
+    npatch = t[f"tess_{name}"].shape[0] // (ninst * nlines * nsub * 2)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=float(t[f"tess_{name}_scale"]))
+        sim.upload(g["pos10"], g["vel10"], g["tan0"])
+        sim.tess_set_patches(g["patch"][:6 * npatch])
+        got = sim.tess_stream(ninst, nlines, nsub, seed=seed)
+    assert_bit_equal(got, t[f"tess_{name}"], "tess-stream vertices vs the reference shader stages")
+
+
+@pytest.mark.gpu
 def test_tess_stream_api_errors():
     with bb.HairSim(8, 4) as sim:
         with pytest.raises(bb.BarbuHairError):
