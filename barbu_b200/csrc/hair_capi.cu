@@ -258,7 +258,12 @@ int bh_init_strands(bh_sim* s, const float* root_pos3, const float* root_nrm3, c
 }
 
 int bh_init_sphere_scalp(bh_sim* s, int rows, int cols, int64_t first, const float* random_value, float maxlength) {
+  return bh_init_sphere_scalp_ordered(s, rows, cols, BH_SCALP_ROW_MAJOR, first, random_value, maxlength);
+}
+
+int bh_init_sphere_scalp_ordered(bh_sim* s, int rows, int cols, int order, int64_t first, const float* random_value, float maxlength) {
   if (!s || !random_value || rows <= 0 || cols <= 0) return fail(BH_ERR_INVALID, "bh_init_sphere_scalp: bad argument");
+  if (order != BH_SCALP_ROW_MAJOR && order != BH_SCALP_COLUMN_MAJOR) return fail(BH_ERR_INVALID, "bh_init_sphere_scalp: unknown strand order");
   if (first < 0 || first + s->nstrands > (int64_t)rows * cols) return fail(BH_ERR_INVALID, "bh_init_sphere_scalp: strand range outside the rows*cols grid");
   DeviceGuard g(s->device);
   int rc = ensure_roots(s); if (rc) return rc;
@@ -284,7 +289,7 @@ int bh_init_sphere_scalp(bh_sim* s, int rows, int cols, int64_t first, const flo
   rc = BH_OK;
   if (e == cudaSuccess) rc = map_gl(s);
   if (e == cudaSuccess && rc == BH_OK) {
-    e = bh::launch_sphere_roots(d_row, d_col, cols, first, s->nstrands, s->root_pos3, s->root_nrm3, s->stream);
+    e = bh::launch_sphere_roots(d_row, d_col, rows, cols, order == BH_SCALP_COLUMN_MAJOR, first, s->nstrands, s->root_pos3, s->root_nrm3, s->stream);
     const float scaleOffset = maxlength / static_cast<float>(s->nverts);
     if (e == cudaSuccess)
       e = bh::launch_expand_strands(s->root_pos3, s->root_nrm3, d_rv, s->nstrands, s->nverts, scaleOffset,

@@ -39,12 +39,14 @@ __global__ void __launch_bounds__(256) expand_strands_kernel(const float* __rest
 // rowtab[2r] = cos(theta_r), rowtab[2r+1] = sin(theta_r); coltab likewise for phi_c; both rounded
 // from libm double on the host, so the only device arithmetic is two exact-rounded products.
 __global__ void __launch_bounds__(256) sphere_roots_kernel(const float* __restrict__ rowtab, const float* __restrict__ coltab,
-                                                           int cols, long long first, long long count,
+                                                           int rows, int cols, int column_major, long long first, long long count,
                                                            float* __restrict__ root_pos3, float* __restrict__ root_nrm3) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
     const long long g = first + j;
-    const long long r = g / cols;
-    const int c = (int)(g - r * cols);
+    // strand order: row-major g = r * cols + c (a latitude circle after the other), or column-major g = c * rows + r
+    // (a meridian after the other: a contiguous strand range is then a longitude wedge that holds every latitude)
+    const long long r = column_major ? g % rows : g / cols;
+    const int c = (int)(column_major ? g / rows : g - r * cols);
     const float ct = rowtab[2 * r], st = rowtab[2 * r + 1];
     const float cp = coltab[2 * c], sp = coltab[2 * c + 1];
     const float nx = __fmul_rn(ct, cp), ny = st, nz = __fmul_rn(ct, sp);
@@ -149,10 +151,10 @@ cudaError_t launch_expand_strands(const float* root_pos3, const float* root_nrm3
   return cudaGetLastError();
 }
 
-cudaError_t launch_sphere_roots(const float* rowtab, const float* coltab, int cols, long long first, long long count,
-                                float* root_pos3, float* root_nrm3, cudaStream_t stream) {
+cudaError_t launch_sphere_roots(const float* rowtab, const float* coltab, int rows, int cols, int column_major, long long first,
+                                long long count, float* root_pos3, float* root_nrm3, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
-  sphere_roots_kernel<<<grid_for(count, 256), 256, 0, stream>>>(rowtab, coltab, cols, first, count, root_pos3, root_nrm3);
+  sphere_roots_kernel<<<grid_for(count, 256), 256, 0, stream>>>(rowtab, coltab, rows, cols, column_major, first, count, root_pos3, root_nrm3);
   return cudaGetLastError();
 }
 

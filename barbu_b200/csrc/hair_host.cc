@@ -106,13 +106,18 @@ int bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, 
   return BH_OK;
 }
 
-int bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri) {
-  if (rows < 1 || cols < 1 || !tri) return BH_ERR_INVALID;
+int bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri) { return bh_sphere_scalp_triangles_ordered(rows, cols, BH_SCALP_ROW_MAJOR, tri); }
+
+int bh_sphere_scalp_triangles_ordered(int rows, int cols, int order, int32_t* tri) {
+  if (rows < 1 || cols < 1 || !tri || (order != BH_SCALP_ROW_MAJOR && order != BH_SCALP_COLUMN_MAJOR)) return BH_ERR_INVALID;
+  if ((int64_t)rows * cols > INT32_MAX) return BH_ERR_OVERFLOW;
+  const bool cm = order == BH_SCALP_COLUMN_MAJOR;
+  auto id = [&](int r, int c) -> int32_t { return cm ? c * rows + r : r * cols + c; };   // the same faces in the same order; only the vertex numbering differs
   size_t t = 0;
   for (int r = 0; r + 1 < rows; ++r)
     for (int c = 0; c < cols; ++c) {
       const int c1 = (c + 1) % cols;
-      const int32_t v00 = r * cols + c, v10 = (r + 1) * cols + c, v01 = r * cols + c1, v11 = (r + 1) * cols + c1;
+      const int32_t v00 = id(r, c), v10 = id(r + 1, c), v01 = id(r, c1), v11 = id(r + 1, c1);
       tri[t++] = v00; tri[t++] = v10; tri[t++] = v01;
       tri[t++] = v01; tri[t++] = v10; tri[t++] = v11;
     }

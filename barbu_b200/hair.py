@@ -20,6 +20,7 @@ from . import _build
 
 BH_OK, BH_ERR_INVALID, BH_ERR_CUDA, BH_ERR_NOT_INITIALIZED, BH_ERR_UNSUPPORTED, BH_ERR_OVERFLOW = range(6)
 BH_MATH_EXACT, BH_MATH_FAST = 0, 1
+BH_SCALP_ROW_MAJOR, BH_SCALP_COLUMN_MAJOR = 0, 1
 BH_PLANE_POSITION, BH_PLANE_VELOCITY, BH_PLANE_TANGENT = 0, 1, 2
 BH_MAX_CAPSULES = 8
 
@@ -28,7 +29,7 @@ ABI_SYMBOLS = (
     "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
-    "bh_sphere_scalp_triangles", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
+    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_step_host", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
@@ -104,6 +105,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_init_sphere_scalp": ([vp, C.c_int, C.c_int, i64, vp, f32], C.c_int),
         "bh_init_tangents_host": ([vp, i64, i64, i64, C.c_int, f32, vp], C.c_int),
         "bh_sphere_scalp_triangles": ([C.c_int, C.c_int, vp], C.c_int),
+        "bh_init_sphere_scalp_ordered": ([vp, C.c_int, C.c_int, C.c_int, i64, vp, f32], C.c_int),
+        "bh_sphere_scalp_triangles_ordered": ([C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "bh_build_patch_indices": ([vp, i64, C.c_int, vp, C.c_int], C.c_int),
         "bh_load_obj_scalp": ([C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)], C.c_int),
         "bh_free": ([vp], None),
@@ -179,9 +182,10 @@ def selftest_math(device: int = 0) -> int:
     return int(bad.value)
 
 
-def sphere_scalp_triangles(rows: int, cols: int) -> np.ndarray:
+def sphere_scalp_triangles(rows: int, cols: int, order: int = 0) -> np.ndarray:
+    """Triangle list of the synthetic sphere scalp; order: BH_SCALP_ROW_MAJOR (0) or BH_SCALP_COLUMN_MAJOR (1) vertex numbering."""
     tri = np.empty((2 * (rows - 1) * cols, 3), np.int32)
-    _check(load_library().bh_sphere_scalp_triangles(rows, cols, _ptr(tri)))
+    _check(load_library().bh_sphere_scalp_triangles_ordered(rows, cols, order, _ptr(tri)))
     return tri
 
 
@@ -318,11 +322,13 @@ class HairSim:
             raise ValueError("one root position, normal and jitter value per strand")
         _check(self._lib.bh_init_strands(self._h, _ptr(p), _ptr(n), _ptr(r), maxlength))
 
-    def init_sphere_scalp(self, rows: int, cols: int, first: int, random_value, maxlength: float = 0.5):
+    def init_sphere_scalp(self, rows: int, cols: int, first: int, random_value, maxlength: float = 0.5, order: int = 0):
+        """Strands [first, first + nstrands) of the rows x cols sphere scalp in strand order `order` (BH_SCALP_ROW_MAJOR:
+        latitude circles, BH_SCALP_COLUMN_MAJOR: meridians — contiguous shards are then balanced longitude wedges)."""
         r = _f32(random_value)
         if r.size != self.nstrands:
             raise ValueError("one jitter value per strand of this shard")
-        _check(self._lib.bh_init_sphere_scalp(self._h, rows, cols, first, _ptr(r), maxlength))
+        _check(self._lib.bh_init_sphere_scalp_ordered(self._h, rows, cols, order, first, _ptr(r), maxlength))
 
     # -- state files / checksums (SURVEY 8f) ---------------------------------------------------
     def checksum(self, plane_mask: int = 7, first_strand: int = 0):

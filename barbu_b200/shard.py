@@ -82,14 +82,18 @@ class HairShard:
     """This rank's shard of a global sphere-scalp hair system: HairSim over [first, first+count)."""
 
     def __init__(self, rows: int, cols: int, nverts: int, world: int, rank: int, device: int, seed: int = 1234,
-                 maxlength: float = 0.5, **params):
+                 maxlength: float = 0.5, order: int = 1, **params):
+        """`order`: strand order of the scalp (hair.BH_SCALP_*). The default, column-major, makes every contiguous shard a
+        longitude wedge with the whole latitude range — the same share of strands lying on the collider on every rank. With
+        row-major order rank = latitude band, and the band over the pole (all strands in contact, the costliest kind of
+        warp-step) sets the frame time of the whole job (measured: profiles/r02_straggler.txt)."""
         from . import hair
-        self.rows, self.cols, self.nverts, self.world, self.rank = rows, cols, nverts, world, rank
+        self.rows, self.cols, self.nverts, self.world, self.rank, self.order = rows, cols, nverts, world, rank, order
         self.first, self.count = shard_range(rows * cols, world, rank)
         self.sim = hair.HairSim(self.count, nverts, device=device)
         if params:
             self.sim.configure(**params)
-        self.sim.init_sphere_scalp(rows, cols, self.first, hair.random_values(seed, self.first, self.count), maxlength)
+        self.sim.init_sphere_scalp(rows, cols, self.first, hair.random_values(seed, self.first, self.count), maxlength, order)
 
     def step(self, dt: float, substeps: int = 1):
         self.sim.step(dt, substeps)

@@ -32,6 +32,26 @@ SPHERE = (0.0, 0.0, 0.0, 0.98)
 SCALE = 1.45                                                    # reference default uScaleFactor
 BYTES_PER_VERTEX_PER_LAUNCH = 64                                # float4 pos+vel read, float4 pos+vel written
 SEED = 1234
+COLUMN_MAJOR = True
+
+
+CPU_SAMPLE_STRANDS = 1 << 17                                     # the CPU arm's bounded sample: 1/8 of the per-GPU workload per step
+CPU_SAMPLE_STEPS, CPU_SAMPLE_WARMUP = 3, 1                       # cpu_baseline inside the GPU arm: same strands, same rule
+
+
+def workload_config(args):
+    """The `config` object of BOTH arms (the driver compares them): what is simulated, not how either arm ran it."""
+    return {"workload": workload_name(args.gpus), "iterations": 8, "strand_order": args.order,
+            "state": f"settled: {args.settle} untimed frames from the cold state before the warm-up steps (GPU arm); "
+                     "the CPU arm steps its sample from the cold state after its own warm-up",
+            "l2": f"state {32 * ROWS * COLS_PER_GPU * NVERTS / 2**30:g} GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
+            "timing": "GPU arm: CUDA events on the launching stream, max over ranks; CPU arm: wall clock around the sampled steps",
+            "cpu_sample": cpu_sample_text(host_threads())}
+
+
+def cpu_sample_text(threads):
+    return (f"first {CPU_SAMPLE_STRANDS} of {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices x {SUBSTEPS} substeps per step, "
+            f"{threads} OpenMP threads, CPU restatement of the reference GLSL (oracle/, bit-exact to the shader source; no GL/llvmpipe in the image)")
 
 
 def workload_name(n_gpus):
@@ -188,8 +208,7 @@ def cpu_reference_time(nstrands_sample, steps, warmup, threads):
     """Time the reference path on the host cores: the CPU oracle (a C restatement of cs_simulation.glsl pinned
     bit-exact to the reference shader source, oracle/_ref) on the first `nstrands_sample` strands of the workload."""
     from oracle import pyoracle as po
-    rows = nstrands_sample // COLS_PER_GPU
-    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU)          # same scalp, first `rows` latitude rows
+    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU, column_major=COLUMN_MAJOR)   # same scalp, same strand order: its first strands
     root_pos, root_nrm = root_pos[:nstrands_sample], root_nrm[:nstrands_sample]
     rv = po.random_values(SEED, nstrands_sample)
     pos, vel = po.init_strands(root_pos, root_nrm, rv, NVERTS)
@@ -203,7 +222,6 @@ def cpu_reference_time(nstrands_sample, steps, warmup, threads):
         for _ in range(SUBSTEPS):
             po.step(pos, vel, nstrands_sample, NVERTS, par, nthreads=threads)
     dt = time.perf_counter() - t0
-    del rows
     return nstrands_sample * NVERTS * SUBSTEPS * steps / dt, dt / steps
 
 
@@ -215,7 +233,7 @@ def reference_source_time(nstrands_sample):
     from oracle import pyoracle as po
     if not po.ref_available(NVERTS):
         return None
-    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU)
+    root_pos, root_nrm, _ = po.sphere_scalp(ROWS, COLS_PER_GPU, column_major=COLUMN_MAJOR)
     root_pos, root_nrm = root_pos[:nstrands_sample], root_nrm[:nstrands_sample]
     pos, vel = po.init_strands(root_pos, root_nrm, po.random_values(SEED, nstrands_sample), NVERTS)
     h = float(np.float32(DT) / np.float32(SUBSTEPS))
@@ -230,19 +248,16 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    sample = 1 << 17                                                     # 1/8 of the per-GPU workload per step
+    sample = CPU_SAMPLE_STRANDS
     value, s_per_step = cpu_reference_time(sample, args.steps, args.warmup, threads)
     src_sample = 1 << 12
     src_value = reference_source_time(src_sample)
-    sample_txt = (f"first {sample} of {ROWS * COLS_PER_GPU} strands x {NVERTS} vertices x {SUBSTEPS} substeps per step, "
-                  f"{threads} OpenMP threads")
+    sample_txt = cpu_sample_text(threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "sample": sample_txt,
-                   "note": "reference GLSL cannot run (no GL/EGL/OSMesa/llvmpipe in the image): CPU restatement of "
-                           "cs_simulation.glsl, bit-exact to the shader source compiled against the reference GLM"},
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,8 +285,13 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     S = ROWS * COLS_PER_GPU                       # strands of this rank
-    cols_total = COLS_PER_GPU * world             # one scalp grid ROWS x cols_total shared by all ranks
-    first = rank * S
+    # one scalp grid ROWS x cols_total shared by all ranks; rank g owns the contiguous strand range [g*S, (g+1)*S): with
+    # column-major strand order a longitude wedge (every rank the same contact load), with row-major a latitude band.
+    # --emulate-rank/--emulate-world: this single GPU plays rank R of a W-GPU job (straggler diagnosis on one GPU).
+    eworld, erank = (args.emulate_world, args.emulate_rank) if args.emulate_world > 0 else (world, rank)
+    cols_total = COLS_PER_GPU * eworld
+    first = erank * S
+    order = bb.BH_SCALP_COLUMN_MAJOR if COLUMN_MAJOR else bb.BH_SCALP_ROW_MAJOR
     V = S * NVERTS
     math = bb.BH_MATH_FAST if args.math == "fast" else bb.BH_MATH_EXACT
 
@@ -290,7 +310,7 @@ def run_gpu(args, rank, world, local_rank):
         """W untimed steps (+ pre-roll so clocks settle), then exactly K steps between two CUDA events on the launching
         stream, barrier + synchronize on both sides, max over ranks. Returns (ms_total, launches)."""
         sim.configure(math=math_id)
-        sim.init_sphere_scalp(ROWS, cols_total, first, rv)        # every profile starts from the same cold state
+        sim.init_sphere_scalp(ROWS, cols_total, first, rv, order=order)   # every profile starts from the same cold state
         for i in range(args.settle):
             sim.step(DT, SUBSTEPS)
             if i % 16 == 15:
@@ -312,8 +332,6 @@ def run_gpu(args, rank, world, local_rank):
             sim.step(DT, SUBSTEPS)
         ev1.record(stream)
         barrier()
-        if sampler is not None:
-            sampler.mark_end()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
         per_rank = [float(ms.item())]
         if dist is not None:
@@ -321,10 +339,31 @@ def run_gpu(args, rank, world, local_rank):
             dist.all_gather(allms, ms)
             per_rank = [float(x.item()) for x in allms]
         per_rank_ms.append(per_rank)
-        return max(per_rank), sim.launch_count - l0
+        launches = sim.launch_count - l0
+        # the same loop again for >= args.sustain seconds: K = 20 frames is 28 ms, shorter than a power-management period
+        sustained = None
+        if args.sustain > 0:
+            n = max(args.steps, int(args.sustain / max(max(per_rank) * 1e-3 / args.steps, 1e-6)) + 1)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            s0.record(stream)
+            for _ in range(n):
+                sim.step(DT, SUBSTEPS)
+            s1.record(stream)
+            barrier()
+            sms = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            sustained = {"steps": n, "seconds": float(sms.item()) * 1e-3, "ms_per_step": float(sms.item()) / n,
+                         "value": world * V * SUBSTEPS * n / (float(sms.item()) * 1e-3), "unit": UNIT}
+        if sampler is not None:
+            sampler.mark_end()
+        sustained_by_math[math_id] = sustained
+        return max(per_rank), launches
 
     # ---- device-resident timing: value + roofline ---------------------------------------------------
     per_rank_ms = []
+    sustained_by_math = {}
     rv = bb.random_values(SEED, first, S)
     kernel_kind = sim.kernel_kind
     sampler = ClockSampler(local_rank)
@@ -412,17 +451,14 @@ def run_gpu(args, rank, world, local_rank):
         achieved = BYTES_PER_VERTEX_PER_LAUNCH * V / per_launch_s / 1e9
         value = world * V * SUBSTEPS * args.steps / (ms_total * 1e-3)
         threads = host_threads()
-        sample = 1 << 19
-        cpu_value, _ = cpu_reference_time(sample, 1, 0, threads) if world == 1 and not args.no_cpu_baseline else (None, None)
+        # the CPU arm's own sampling rule (bench.py --impl reference): same strands, same warm-up, same steps
+        cpu_value, _ = cpu_reference_time(CPU_SAMPLE_STRANDS, args.steps, args.warmup, threads) if world == 1 and not args.no_cpu_baseline else (None, None)
         kernel_names = {0: "hair_step_stream_kernel", 1: "hair_step_pipelined_kernel", 2: "hair_step_generic_kernel"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(world), "math": args.math, "iterations": 8,
-                       "state": f"settled: {args.settle} untimed frames from the cold state, then {args.warmup}+ warm-up steps",
-                       "l2": f"state {32 * V / 2**30:g} GiB per GPU > 126 MB L2: every launch streams from HBM (no flush needed)",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": workload_config(args), "math": args.math,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": kernel_names.get(kernel_kind, "?"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V, "ms_per_launch": per_launch_s * 1e3},
@@ -437,9 +473,8 @@ def run_gpu(args, rank, world, local_rank):
         if world > 1:
             line["ms_per_step_by_rank"] = [t / args.steps for t in per_rank_ms[0]]
         if cpu_value is not None:
-            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"first {sample} of {S} strands x {NVERTS} vertices x {SUBSTEPS} substeps, 1 step, "
-                                              f"{threads} OpenMP threads; CPU restatement of the reference GLSL, not llvmpipe"}
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(threads),
+                                    "steps": args.steps, "warmup": args.warmup}
         traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.exists(traffic_file):
@@ -448,6 +483,12 @@ def run_gpu(args, rank, world, local_rank):
         if S != 1 << 20:
             traffic = {}                                      # the ncu capture is of the configs[1] launch
         line["roofline"]["traffic"] = traffic.get(args.math)
+        line["roofline"]["traffic_source"] = ("profiles/traffic_bytes_per_launch.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                              "`ncu --set full` capture of this launch shape; static, not measured in this run)") if traffic.get(args.math) else None
+        if sustained_by_math.get(math) is not None:
+            line["sustained"] = dict(sustained_by_math[math], note="the timed loop continued for >= --sustain seconds, same events and rules")
+        if args.emulate_world > 0:
+            line["emulated_shard"] = {"rank": erank, "world": eworld, "order": args.order}
         if other is not None:
             ms2, launches2, clocks2 = other
             name2 = "exact" if args.math == "fast" else "fast"
@@ -455,6 +496,7 @@ def run_gpu(args, rank, world, local_rank):
             ach2 = BYTES_PER_VERTEX_PER_LAUNCH * V / per2 / 1e9
             line["other_profile"] = {"math": name2, "value": world * V * SUBSTEPS * args.steps / (ms2 * 1e-3), "unit": UNIT,
                                      "ms_per_step": ms2 / args.steps, "gpu_launches": launches2, "clocks": clocks2,
+                                     "sustained": sustained_by_math.get(other_math),
                                      "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
                                                   "traffic": traffic.get(name2), "ms_per_launch": per2 * 1e3},
                                      "note": "same workload, steps and timing rules; exact = bit-identical to the CPU oracle, "
@@ -485,11 +527,18 @@ def main():
                     help="untimed frames run before the W warm-up steps so that the timed region sees the SETTLED hair (strands "
                          "draped over the collider, push-outs in ~40%% of warp-steps), not the cold straight state, which is "
                          "cheaper for the exact profile (0 for profiler runs that want the cold state)")
+    ap.add_argument("--order", default="column", choices=["column", "row"],
+                    help="strand order of the sphere scalp: column = meridian by meridian (contiguous shards are balanced longitude "
+                         "wedges), row = latitude circle by circle (round 1: shard = latitude band, the polar band straggles)")
+    ap.add_argument("--sustain", type=float, default=0.25, help="seconds the timed loop is continued for the `sustained` figure (0: off)")
+    ap.add_argument("--emulate-world", type=int, default=0, help="with --emulate-rank: run that rank's shard of a W-GPU job on this one GPU")
+    ap.add_argument("--emulate-rank", type=int, default=0)
     ap.add_argument("--log2-strands", type=int, default=20,
                     help="strands per GPU = 2^k (default 20 = configs[1]; 23 = the per-GPU shard of configs[3], 64M strands over 8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    global ROWS, COLS_PER_GPU
+    global ROWS, COLS_PER_GPU, COLUMN_MAJOR
+    COLUMN_MAJOR = args.order == "column"
     ROWS = 1 << (args.log2_strands // 2)
     COLS_PER_GPU = (1 << args.log2_strands) // ROWS
     rank = int(os.environ.get("RANK", "0"))

@@ -96,6 +96,16 @@ int  bh_init_strands(bh_sim* sim, const float* root_pos3, const float* root_nrm3
  * [first, first+nstrands). Roots are generated on the device, then expanded as bh_init_strands. */
 int  bh_init_sphere_scalp(bh_sim* sim, int rows, int cols, int64_t first,
                           const float* random_value, float maxlength);
+/* Same scalp with a chosen STRAND ORDER (= vertex numbering of the scalp mesh; the reference takes strands in mesh vertex
+ * order, hair.cc:255-287). BH_SCALP_ROW_MAJOR: strand g = r * cols + c, one latitude circle after the other (the plain
+ * calls above). BH_SCALP_COLUMN_MAJOR: strand g = c * rows + r, one meridian after the other — a contiguous strand range is
+ * then a longitude wedge that holds every latitude, so contiguous shards carry the same collider-contact
+ * load instead of one rank owning the pole where all hair lies on the collider. random_value[j] belongs to strand
+ * first + j in the chosen order (bh_random_values(seed, first, count): one rand() per strand in strand order). */
+enum { BH_SCALP_ROW_MAJOR = 0, BH_SCALP_COLUMN_MAJOR = 1 };
+int  bh_init_sphere_scalp_ordered(bh_sim* sim, int rows, int cols, int order, int64_t first,
+                                  const float* random_value, float maxlength);
+int  bh_sphere_scalp_triangles_ordered(int rows, int cols, int order, int32_t* tri_indices);
 /* hair.cc:290-328: tangent plane, host-evaluated (libm sinf/cosf + glm::simplex restated), for
  * global strands [first, first+count) out of `total`. Output: count*nverts float4. */
 int  bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, int64_t count,

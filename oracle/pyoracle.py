@@ -86,11 +86,18 @@ def random_values(seed: int, nstrands: int) -> np.ndarray:
     return out
 
 
-def sphere_scalp(rows: int, cols: int):
+def sphere_scalp(rows: int, cols: int, column_major: bool = False):
+    """Synthetic sphere scalp. column_major: the same mesh with its vertices numbered meridian by meridian
+    (vertex c * rows + r instead of r * cols + c); faces keep their order."""
     S = rows * cols
     pos, nrm = np.empty((S, 3), np.float32), np.empty((S, 3), np.float32)
     tri = np.empty((2 * (rows - 1) * cols, 3), np.int32)
     oracle().bho_sphere_scalp(C.c_int(rows), C.c_int(cols), _p(pos), _p(nrm), _p(tri))
+    if column_major:
+        old_of_new = np.arange(S).reshape(rows, cols).T.reshape(-1)          # new vertex c * rows + r  <-  old r * cols + c
+        new_of_old = np.empty(S, np.int64); new_of_old[old_of_new] = np.arange(S)
+        pos, nrm = np.ascontiguousarray(pos[old_of_new]), np.ascontiguousarray(nrm[old_of_new])
+        tri = new_of_old[tri].astype(np.int32)
     return pos, nrm, tri
 
 

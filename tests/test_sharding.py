@@ -84,17 +84,37 @@ def test_sharded_run_plus_allgather_equals_single_run_gloo(world, rows, cols, tm
     assert_bit_equal(np.load(out), pos, "gathered position plane == single-process run")
 
 
+def test_column_major_scalp_is_the_same_mesh_renumbered():
+    """BH_SCALP_COLUMN_MAJOR (strand c * rows + r): the product's host triangle list against the oracle's renumbered scalp,
+    and the property that makes it the balanced partition — every contiguous shard holds every latitude row equally often."""
+    rows, cols = 12, 16
+    pos_r, _, tri_r = po.sphere_scalp(rows, cols)
+    pos_c, _, tri_c = po.sphere_scalp(rows, cols, column_major=True)
+    assert_bit_equal(bb.sphere_scalp_triangles(rows, cols, bb.BH_SCALP_COLUMN_MAJOR), tri_c, "column-major triangles")
+    assert_bit_equal(bb.sphere_scalp_triangles(rows, cols, bb.BH_SCALP_ROW_MAJOR), tri_r, "row-major triangles")
+    assert_bit_equal(pos_c[tri_c], pos_r[tri_r], "same faces, same corner positions, same face order")
+    for world in (2, 4, 8):
+        for rank in range(world):
+            first, count = shard.shard_range(rows * cols, world, rank)
+            lat = np.arange(first, first + count) % rows                 # latitude row of each strand of the shard
+            assert (np.bincount(lat, minlength=rows) == cols // world).all()
+    with pytest.raises(bb.BarbuHairError):
+        bb.sphere_scalp_triangles(rows, cols, 7)
+
+
 @pytest.mark.gpu
-def test_hair_shard_on_device_matches_global_run():
-    """Two shards stepped independently on the device == the oracle stepping the whole scalp (zero exchange steps)."""
+@pytest.mark.parametrize("order", [0, 1])
+def test_hair_shard_on_device_matches_global_run(order):
+    """Two shards stepped independently on the device == the oracle stepping the whole scalp (zero exchange steps), for
+    both strand orders (row-major: latitude bands; column-major: longitude wedges)."""
     rows, cols, N = 32, 64, 16
-    _, _, _, _, pos, vel = sphere_state(rows, cols, N)
+    _, _, _, _, pos, vel = sphere_state(rows, cols, N, column_major=bool(order))
     par = po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE)
     for _ in range(3):
         po.step(pos, vel, rows * cols, N, par)
     got = []
     for rank in range(2):
-        sh = shard.HairShard(rows, cols, N, 2, rank, device=0, scale=1.45, sphere=SPHERE)
+        sh = shard.HairShard(rows, cols, N, 2, rank, device=0, order=order, scale=1.45, sphere=SPHERE)
         for _ in range(3):
             sh.step(float(DT), 1)
         sh.sim.synchronize()

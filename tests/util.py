@@ -33,9 +33,9 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
-def sphere_state(rows, cols, nverts, seed=1234, maxlength=0.5):
+def sphere_state(rows, cols, nverts, seed=1234, maxlength=0.5, column_major=False):
     """Oracle-built initial state of a rows x cols sphere scalp: (root_pos, root_nrm, tri, rv, pos, vel)."""
-    root_pos, root_nrm, tri = po.sphere_scalp(rows, cols)
+    root_pos, root_nrm, tri = po.sphere_scalp(rows, cols, column_major)
     rv = po.random_values(seed, rows * cols)
     pos, vel = po.init_strands(root_pos, root_nrm, rv, nverts, maxlength)
     return root_pos, root_nrm, tri, rv, pos, vel
