@@ -98,6 +98,7 @@ using bh::unmap_gl;
 extern "C" {
 
 const char* bh_last_error(void) { return g_last_error.c_str(); }
+int bh_host_fail_impl(int code, const char* what) { return fail(code, what); }      // for hair_host.cc (no CUDA headers there)
 const char* bh_version(void) { return "barbu_hair 0.1 (sm_100a)"; }
 
 void bh_default_params(bh_params* p) {

@@ -60,20 +60,38 @@ float simplex2(float vx, float vy) {
 
 }  // namespace
 
+// errors of the host-only entry points reach bh_last_error() like those of the CUDA ones (hair_capi.cu)
+extern "C" int bh_host_fail_impl(int code, const char* what);
+static int bh_host_fail(int code, const char* what) { return bh_host_fail_impl(code, what); }
+
 extern "C" {
 
+// glibc's rand() is random() on the TYPE_3 additive-feedback generator (128 bytes of state). The reentrant form of the
+// same generator (initstate_r / random_r, stdlib.h) yields the same sequence from a PRIVATE state: the host application's
+// own rand() stream — the reference seeds it once with time() and its other modules draw from it (core/app.cc:96-97) — is
+// neither reseeded nor consumed, and concurrent callers do not race. The state is kept per thread together with its
+// position in the sequence, so shard after shard of one scalp (ascending `first`, same seed) costs O(count), not O(first).
 int bh_random_values(unsigned seed, int64_t first, int64_t count, float* out) {
-  if (first < 0 || count < 0 || (count > 0 && !out)) return BH_ERR_INVALID;
-  srand(seed);                                                            // stands in for app.cc:96-97
-  for (int64_t j = 0; j < first; ++j) (void)rand();
-  for (int64_t j = 0; j < count; ++j)
-    out[j] = static_cast<float>(1.0 + 0.1 * (1.0 - 2.0 * static_cast<double>(rand()) / static_cast<double>(RAND_MAX)));
+  if (first < 0 || count < 0 || (count > 0 && !out)) return bh_host_fail(BH_ERR_INVALID, "bh_random_values: bad argument");
+  struct Gen { struct random_data rd; char state[128]; unsigned seed; int64_t pos; bool live; };
+  static thread_local Gen g = {};
+  if (!g.live || g.seed != seed || g.pos > first) {
+    std::memset(&g.rd, 0, sizeof g.rd);
+    if (initstate_r(seed, g.state, sizeof g.state, &g.rd) != 0) return bh_host_fail(BH_ERR_INVALID, "bh_random_values: initstate_r failed");
+    g.seed = seed; g.pos = 0; g.live = true;
+  }
+  int32_t r = 0;
+  for (; g.pos < first; ++g.pos) (void)random_r(&g.rd, &r);
+  for (int64_t j = 0; j < count; ++j, ++g.pos) {
+    (void)random_r(&g.rd, &r);                                            // == rand() after srand(seed), hair.cc:273-275
+    out[j] = static_cast<float>(1.0 + 0.1 * (1.0 - 2.0 * static_cast<double>(r) / static_cast<double>(RAND_MAX)));
+  }
   return BH_OK;
 }
 
 int bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, int64_t count, int nverts,
                           float maxlength, float* tan4) {
-  if (!root_nrm3 || !tan4 || total <= 0 || first < 0 || count < 0 || first + count > total || nverts < 1) return BH_ERR_INVALID;
+  if (!root_nrm3 || !tan4 || total <= 0 || first < 0 || count < 0 || first + count > total || nverts < 1) return bh_host_fail(BH_ERR_INVALID, "bh_init_tangents_host: bad argument");
   const int N = nverts;
   const float inv_nroots = 1.0f / static_cast<float>(total);              // hair.cc:292
   const float kPi = static_cast<float>(3.14159265358979323846264338327950288);             // glm::pi<float>()
@@ -109,8 +127,8 @@ int bh_init_tangents_host(const float* root_nrm3, int64_t total, int64_t first, 
 int bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri) { return bh_sphere_scalp_triangles_ordered(rows, cols, BH_SCALP_ROW_MAJOR, tri); }
 
 int bh_sphere_scalp_triangles_ordered(int rows, int cols, int order, int32_t* tri) {
-  if (rows < 1 || cols < 1 || !tri || (order != BH_SCALP_ROW_MAJOR && order != BH_SCALP_COLUMN_MAJOR)) return BH_ERR_INVALID;
-  if ((int64_t)rows * cols > INT32_MAX) return BH_ERR_OVERFLOW;
+  if (rows < 1 || cols < 1 || !tri || (order != BH_SCALP_ROW_MAJOR && order != BH_SCALP_COLUMN_MAJOR)) return bh_host_fail(BH_ERR_INVALID, "bh_sphere_scalp_triangles: bad argument");
+  if ((int64_t)rows * cols > INT32_MAX) return bh_host_fail(BH_ERR_OVERFLOW, "bh_sphere_scalp_triangles: vertex ids exceed int32");
   const bool cm = order == BH_SCALP_COLUMN_MAJOR;
   auto id = [&](int r, int c) -> int32_t { return cm ? c * rows + r : r * cols + c; };   // the same faces in the same order; only the vertex numbering differs
   size_t t = 0;
@@ -133,10 +151,10 @@ int bh_sphere_scalp_triangles_ordered(int rows, int cols, int order, int32_t* tr
 // (src/fx/hair.cc:58). A scalp without normals would get per-corner normals from recalculateNormals
 // (src/utils/raw_mesh_file.cc:11-50) and 3 strands per face; that path is not restated: BH_ERR_UNSUPPORTED.
 int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nvertices, int32_t** tri, int64_t* nfaces) {
-  if (!path || !pos3 || !nrm3 || !nvertices || !tri || !nfaces) return BH_ERR_INVALID;
+  if (!path || !pos3 || !nrm3 || !nvertices || !tri || !nfaces) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: NULL argument");
   *pos3 = *nrm3 = nullptr; *tri = nullptr; *nvertices = *nfaces = 0;
   FILE* f = std::fopen(path, "rb");
-  if (!f) return BH_ERR_INVALID;                                           // "The scalp mesh resource was not found." (hair.cc:45-48)
+  if (!f) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: cannot open the file");                                           // "The scalp mesh resource was not found." (hair.cc:45-48)
   std::string text;
   char buf[1 << 16];
   for (size_t n; (n = std::fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, n);
@@ -168,7 +186,7 @@ int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nve
       if (e.v > 0) { corners.push_back(c); corners.push_back(e); corners.push_back(a); }
     }
   }
-  if (corners.empty() || positions.empty()) return BH_ERR_INVALID;
+  if (corners.empty() || positions.empty()) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: no faces or no positions in the file");
   if (normals.empty()) return BH_ERR_UNSUPPORTED;
   std::map<std::tuple<int, int, int>, int32_t> seen;
   std::vector<I3> unique;
@@ -176,7 +194,7 @@ int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nve
   indices.reserve(corners.size());
   for (const I3& c0 : corners) {
     const I3 c{ c0.v - 1, c0.t - 1, c0.n - 1 };                            // [1, n] -> [0, n-1]; absent attributes become -1
-    if (c.v < 0 || (size_t)c.v >= positions.size() || c.n < 0 || (size_t)c.n >= normals.size()) return BH_ERR_INVALID;
+    if (c.v < 0 || (size_t)c.v >= positions.size() || c.n < 0 || (size_t)c.n >= normals.size()) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: face index outside the v / vn lists");
     auto key = std::make_tuple(c.v, c.t, c.n);
     auto it = seen.find(key);
     if (it == seen.end()) { it = seen.emplace(key, (int32_t)unique.size()).first; unique.push_back(c); }
@@ -186,7 +204,7 @@ int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nve
   float* P = static_cast<float*>(std::malloc(sizeof(float) * 3 * nv));
   float* Nn = static_cast<float*>(std::malloc(sizeof(float) * 3 * nv));
   int32_t* T = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * 3 * nf));
-  if (!P || !Nn || !T) { std::free(P); std::free(Nn); std::free(T); return BH_ERR_INVALID; }
+  if (!P || !Nn || !T) { std::free(P); std::free(Nn); std::free(T); return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: out of host memory"); }
   for (size_t j = 0; j < nv; ++j) {
     const V3 &p = positions[unique[j].v], &n = normals[unique[j].n];
     P[3 * j] = p.x; P[3 * j + 1] = p.y; P[3 * j + 2] = p.z;

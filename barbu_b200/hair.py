@@ -34,6 +34,10 @@ ABI_SYMBOLS = (
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
     "bh_marschner_default_params", "bh_marschner_generate",
+    "bh_group_create", "bh_group_destroy", "bh_group_size", "bh_group_shard", "bh_group_shard_range", "bh_group_set_params",
+    "bh_group_set_bounding_sphere", "bh_group_init_sphere_scalp", "bh_group_init_strands", "bh_group_upload", "bh_group_download",
+    "bh_group_step", "bh_group_synchronize", "bh_group_step_timed", "bh_group_launch_count", "bh_group_gather_plane",
+    "bh_group_register_gl_buffer", "bh_group_unregister_gl_buffer", "bh_group_gather_to_gl",
 )
 
 
@@ -129,6 +133,25 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_save_state": ([vp, C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
         "bh_peek_state": ([C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
         "bh_load_state": ([vp, C.c_char_p, C.POINTER(BhStateInfo)], C.c_int),
+        "bh_group_create": ([C.POINTER(vp), C.POINTER(C.c_int), C.c_int, i64, C.c_int], C.c_int),
+        "bh_group_destroy": ([vp], C.c_int),
+        "bh_group_size": ([vp], C.c_int),
+        "bh_group_shard": ([vp, C.c_int], vp),
+        "bh_group_shard_range": ([vp, C.c_int, C.POINTER(i64), C.POINTER(i64)], C.c_int),
+        "bh_group_set_params": ([vp, C.POINTER(BhParams)], C.c_int),
+        "bh_group_set_bounding_sphere": ([vp, C.POINTER(f32)], C.c_int),
+        "bh_group_init_sphere_scalp": ([vp, C.c_int, C.c_int, C.c_int, C.c_uint, f32], C.c_int),
+        "bh_group_init_strands": ([vp, vp, vp, vp, f32], C.c_int),
+        "bh_group_upload": ([vp, vp, vp, vp], C.c_int),
+        "bh_group_download": ([vp, vp, vp, vp], C.c_int),
+        "bh_group_step": ([vp, f32, C.c_int], C.c_int),
+        "bh_group_synchronize": ([vp], C.c_int),
+        "bh_group_step_timed": ([vp, f32, C.c_int, C.c_int, C.POINTER(f32), C.POINTER(f32)], C.c_int),
+        "bh_group_launch_count": ([vp], i64),
+        "bh_group_gather_plane": ([vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(f32)], C.c_int),
+        "bh_group_register_gl_buffer": ([vp, C.c_uint, C.c_int], C.c_int),
+        "bh_group_unregister_gl_buffer": ([vp], C.c_int),
+        "bh_group_gather_to_gl": ([vp, C.c_uint], C.c_int),
         "bh_last_error": ([], C.c_char_p),
         "bh_version": ([], C.c_char_p),
     }
@@ -137,6 +160,16 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         fn.argtypes, fn.restype = argtypes, restype
     _lib = lib
     return lib
+
+
+def _apply_param_keywords(p, kw) -> None:
+    for k, v in kw.items():
+        cur = getattr(p, k)
+        if isinstance(cur, C.Array) and not isinstance(v, C.Array):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
 
 
 def _check(rc: int) -> None:
@@ -269,13 +302,7 @@ class HairSim:
     def configure(self, **kw):
         """Update named fields of bh_params (scale=..., math=..., sphere=(x,y,z,r), ...)."""
         p = self.get_params()
-        for k, v in kw.items():
-            cur = getattr(p, k)
-            if isinstance(cur, C.Array) and not isinstance(v, C.Array):
-                for i, x in enumerate(v):
-                    cur[i] = x
-            else:
-                setattr(p, k, v)
+        _apply_param_keywords(p, kw)
         self.set_params(p)
 
     def set_bounding_sphere(self, sphere: Sequence[float]):
@@ -409,6 +436,106 @@ class HairSim:
 
     def unregister_gl_buffer(self):
         _check(self._lib.bh_unregister_gl_buffer(self._h))
+
+
+class HairGroup:
+    """One scalp sharded over several GPUs behind one handle and one host thread (bh_group_*, include/barbu_hair.h): contiguous
+    strand ranges, asynchronous per-device launches, no per-step exchange; optional peer-copy gather of a plane to one GPU."""
+
+    def __init__(self, devices, nstrands: int, nverts: int):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(self._lib.bh_group_create(C.byref(self._h), devs, len(devices), nstrands, nverts))
+        self.devices, self.nstrands, self.nverts = list(devices), nstrands, nverts
+        self.nvertices = nstrands * nverts
+
+    def close(self):
+        if self._h:
+            self._lib.bh_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return self._lib.bh_group_size(self._h)
+
+    def shard_range(self, g: int):
+        first, count = C.c_int64(), C.c_int64()
+        _check(self._lib.bh_group_shard_range(self._h, g, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def configure(self, **kw):
+        """Same keywords as HairSim.configure, applied to every shard."""
+        p = default_params()
+        shard0 = self._lib.bh_group_shard(self._h, 0)
+        _check(self._lib.bh_get_params(shard0, C.byref(p)))
+        _apply_param_keywords(p, kw)
+        _check(self._lib.bh_group_set_params(self._h, C.byref(p)))
+
+    def set_bounding_sphere(self, sphere):
+        _check(self._lib.bh_group_set_bounding_sphere(self._h, (C.c_float * 4)(*sphere)))
+
+    def init_sphere_scalp(self, rows: int, cols: int, order: int = BH_SCALP_COLUMN_MAJOR, seed: int = 1234, maxlength: float = 0.5):
+        _check(self._lib.bh_group_init_sphere_scalp(self._h, rows, cols, order, seed, maxlength))
+
+    def init_strands(self, root_pos3, root_nrm3, random_value, maxlength: float = 0.5):
+        p, n, r = _f32(root_pos3, 3), _f32(root_nrm3, 3), _f32(random_value)
+        if p.shape[0] != self.nstrands or n.shape[0] != self.nstrands or r.size != self.nstrands:
+            raise ValueError("one root, one normal and one jitter value per strand of the whole scalp")
+        _check(self._lib.bh_group_init_strands(self._h, _ptr(p), _ptr(n), _ptr(r), maxlength))
+
+    def upload(self, pos4=None, vel4=None, tan4=None):
+        arrs = [None if a is None else _f32(a) for a in (pos4, vel4, tan4)]
+        for a in arrs:
+            if a is not None and a.size != 4 * self.nvertices:
+                raise ValueError("global planes: 4 floats per vertex of the whole scalp")
+        _check(self._lib.bh_group_upload(self._h, *[_ptr(a) for a in arrs]))
+
+    def download(self):
+        out = [np.empty((self.nvertices, 4), np.float32) for _ in range(3)]
+        _check(self._lib.bh_group_download(self._h, *[_ptr(a) for a in out]))
+        return tuple(out)
+
+    def step(self, dt: float, substeps: int = 1):
+        _check(self._lib.bh_group_step(self._h, dt, substeps))
+
+    def synchronize(self):
+        _check(self._lib.bh_group_synchronize(self._h))
+
+    def step_timed(self, dt: float, substeps: int, frames: int):
+        """(max ms, [ms per shard]) of `frames` frames, measured with CUDA events on each device."""
+        mx = C.c_float()
+        per = (C.c_float * self.size)()
+        _check(self._lib.bh_group_step_timed(self._h, dt, substeps, frames, C.byref(mx), per))
+        return mx.value, list(per)
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.bh_group_launch_count(self._h)
+
+    def gather_plane(self, plane: int = BH_PLANE_POSITION, dst_device: int = 0):
+        """(device pointer, ms): plane of the whole scalp on dst_device, gathered by peer copies."""
+        ptr, ms = C.c_void_p(), C.c_float()
+        _check(self._lib.bh_group_gather_plane(self._h, plane, dst_device, C.byref(ptr), C.byref(ms)))
+        return ptr.value, ms.value
+
+    def register_gl_buffer(self, gl_buffer: int, render_device: int = 0):
+        _check(self._lib.bh_group_register_gl_buffer(self._h, gl_buffer, render_device))
+
+    def gather_to_gl(self, plane_mask: int = 1):
+        _check(self._lib.bh_group_gather_to_gl(self._h, plane_mask))
 
 
 @dataclass

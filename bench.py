@@ -508,6 +508,60 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_group(args):
+    """--single-process: the same weak-scaling job through the C ABI's group API (bh_group_*): ONE process, ONE host thread,
+    args.gpus devices — the form the reference's single-threaded frame loop can call. Timed with per-device CUDA events
+    (bh_group_step_timed), max over shards; the optional gather of the position plane to device 0 is timed separately."""
+    import torch
+    import barbu_b200 as bb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hair simulation has no CPU path")
+    G = args.gpus
+    devices = list(range(G)) if torch.cuda.device_count() >= G else [i % torch.cuda.device_count() for i in range(G)]
+    S_total = ROWS * COLS_PER_GPU * G
+    V_shard = ROWS * COLS_PER_GPU * NVERTS
+    math = bb.BH_MATH_FAST if args.math == "fast" else bb.BH_MATH_EXACT
+    grp = bb.HairGroup(devices, S_total, NVERTS)
+    grp.configure(scale=SCALE, sphere=SPHERE, math=math)
+    grp.init_sphere_scalp(ROWS, COLS_PER_GPU * G, order=bb.BH_SCALP_COLUMN_MAJOR if COLUMN_MAJOR else bb.BH_SCALP_ROW_MAJOR, seed=SEED)
+    for i in range(args.settle + args.warmup):
+        grp.step(DT, SUBSTEPS)
+        if i % 16 == 15:
+            grp.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.mark_begin()
+    l0 = grp.launch_count
+    ms_total, per = grp.step_timed(DT, SUBSTEPS, args.steps)
+    launches = grp.launch_count - l0
+    sampler.mark_end()
+    clocks = sampler.stop()
+    gather = None
+    if G > 1:
+        grp.gather_plane(0, devices[0])
+        gms = min(grp.gather_plane(0, devices[0])[1] for _ in range(5))
+        recv = 16 * V_shard * (G - 1) if len(set(devices)) > 1 else 0
+        gather = {"ms": gms, "bytes_received_by_render_gpu": recv, "gbs": recv / (gms * 1e-3) / 1e9 if gms > 0 else None,
+                  "nvlink_reference_gbs": 770.0, "what": "bh_group_gather_plane: position plane of every shard pushed to device 0 by "
+                  "cudaMemcpyPeerAsync over NVLink (optional, off the per-step path); 770 GB/s = measured per-direction NVLink figure of SURVEY.md §5"}
+    grp.close()
+    peak, peak_src = peaks()
+    per_launch_s = ms_total * 1e-3 / (launches / G)
+    achieved = BYTES_PER_VERTEX_PER_LAUNCH * V_shard / per_launch_s / 1e9
+    line = {"metric": METRIC, "value": G * V_shard * SUBSTEPS * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": G, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args), "math": args.math,
+            "mode": "single process, one host thread, bh_group_* (C ABI)", "devices": devices,
+            "ms_per_step_by_shard": [t / args.steps for t in per],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "hair_step_stream_kernel", "peak_source": peak_src, "per": "GPU (slowest shard)",
+                         "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V_shard, "ms_per_launch": per_launch_s * 1e3},
+            "gpu_launches": launches, "clocks": clocks}
+    if gather:
+        line["gather"] = gather
+    emit(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -527,6 +581,9 @@ def main():
                     help="untimed frames run before the W warm-up steps so that the timed region sees the SETTLED hair (strands "
                          "draped over the collider, push-outs in ~40%% of warp-steps), not the cold straight state, which is "
                          "cheaper for the exact profile (0 for profiler runs that want the cold state)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus devices from this one process and host thread through the C ABI's group API (bh_group_*) "
+                         "instead of one rank per GPU under torch.distributed.run")
     ap.add_argument("--order", default="column", choices=["column", "row"],
                     help="strand order of the sphere scalp: column = meridian by meridian (contiguous shards are balanced longitude "
                          "wedges), row = latitude circle by circle (round 1: shard = latitude band, the polar band straggles)")
@@ -553,6 +610,8 @@ def main():
     _emit_fd = real_stdout
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.single_process:
+        run_group(args)
     else:
         run_gpu(args, rank, world, local_rank)
     sys.stdout.flush()

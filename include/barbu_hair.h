@@ -211,6 +211,44 @@ void bh_marschner_default_params(bh_marschner_params* p);
 int  bh_marschner_generate(const bh_marschner_params* p, int resolution, int device, uint16_t* m_rgba16f,
                            uint16_t* n_rgba16f, float* m_rgba32f, float* n_rgba32f);
 
+/* ---- one scalp over several GPUs, behind one handle, from ONE host thread (SURVEY.md §8b "Threading", §8e) ------------- */
+/* The reference's host is one process and one thread (src/core/app.cc:60-81, core/renderer.cc:69-81): it cannot use ranks.
+ * A group shards the strand set contiguously — shard g = global strands [S*g/G, S*(g+1)/G) on devices[g] (a device may be
+ * listed more than once) — and steps all shards with asynchronous launches on their own streams; no step exchanges data
+ * (strands are independent, cs_simulation.glsl:170-208). Global planes passed to upload / download are in global strand
+ * order (vertex = strand * nverts + i), exactly the single-device layout. The ONE exchange is optional: gathering a plane
+ * of buffer 0 onto the render GPU, pushed by every source GPU with peer copies over NVLink / NVSwitch, so that the render
+ * VAO (hair.cc:371-389) sees the whole scalp. bh_group_shard() lends a shard's bh_sim for every per-shard call above. */
+typedef struct bh_group bh_group;
+int     bh_group_create(bh_group** out, const int* devices, int ndevices, int64_t nstrands, int nverts);
+int     bh_group_destroy(bh_group* group);
+int     bh_group_size(const bh_group* group);
+bh_sim* bh_group_shard(bh_group* group, int shard);                                   /* borrowed; NULL when out of range */
+int     bh_group_shard_range(const bh_group* group, int shard, int64_t* first, int64_t* count);
+int     bh_group_set_params(bh_group* group, const bh_params* p);
+int     bh_group_set_bounding_sphere(bh_group* group, const float sphere[4]);         /* Hair::set_bounding_sphere for every shard */
+int     bh_group_init_sphere_scalp(bh_group* group, int rows, int cols, int order, unsigned seed, float maxlength);
+int     bh_group_init_strands(bh_group* group, const float* root_pos3, const float* root_nrm3, const float* random_value,
+                              float maxlength);                                       /* global arrays, one entry per strand */
+int     bh_group_upload(bh_group* group, const float* pos4, const float* vel4, const float* tan4);   /* global planes */
+int     bh_group_download(bh_group* group, float* pos4, float* vel4, float* tan4);
+int     bh_group_step(bh_group* group, float dt, int substeps);                       /* Hair::update(dt); returns after the launches */
+int     bh_group_synchronize(bh_group* group);
+/* `frames` x bh_group_step between per-device CUDA events: ms_per_shard[g] (may be NULL) and their maximum — the frame
+ * time of the job, measured on the devices. */
+int     bh_group_step_timed(bh_group* group, float dt, int substeps, int frames, float* ms_max, float* ms_per_shard);
+int64_t bh_group_launch_count(const bh_group* group);
+/* Gather plane `plane` of every shard into one buffer of V float4 on dst_device (owned by the group, PingPongBuffer layout:
+ * *device_ptr = base of that plane). Ordered after the steps already queued; returns when the buffer is complete.
+ * ms (may be NULL): max over shards of the copy's device time. */
+int     bh_group_gather_plane(bh_group* group, int plane, int dst_device, void** device_ptr, float* ms);
+/* The render GPU's GL buffer 0 (pbuffer_.read_ssbo_id(), 3 planes of the WHOLE scalp) as the gather target:
+ * cudaGraphicsGLRegisterBuffer on render_device; bh_group_gather_to_gl maps it, gathers the planes in plane_mask
+ * (0 = positions only) to their PingPongBuffer offsets and unmaps. Needs a current GL context on the calling thread. */
+int     bh_group_register_gl_buffer(bh_group* group, unsigned int gl_buffer, int render_device);
+int     bh_group_unregister_gl_buffer(bh_group* group);
+int     bh_group_gather_to_gl(bh_group* group, unsigned plane_mask);
+
 /* ---- CUDA-GL interop on buffer 0 (pbuffer_.read_ssbo_id(), hair.cc:371) --------------------- */
 /* cudaGraphicsGLRegisterBuffer; while registered, bh_step maps the GL buffer, steps in place and
  * unmaps, so the render VAO (hair.cc:371-389) sees the new positions without a copy. Needs a

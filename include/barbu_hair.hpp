@@ -46,6 +46,9 @@ class Hair {
       int substeps = 1;               // 1 == reference (one dispatch per frame)
       int math = BH_MATH_EXACT;
       int device = 0;
+      // More than one entry: the strand set is sharded contiguously over these CUDA devices (bh_group_*, one host thread,
+      // no per-step exchange); the render GPU is devices[0]. Empty or one entry: the single-device path on `device`.
+      std::vector<int> devices;
     } b200;
   };
 
@@ -63,6 +66,7 @@ class Hair {
   /* Release all allocated resources (hair.cc:66-87). */
   void deinit() {
     if (sim_) { bh_destroy(sim_); sim_ = nullptr; }
+    if (group_) { bh_group_destroy(group_); group_ = nullptr; }
     patches_uploaded_ = false;
     nroots_ = 0;
     patch_indices_.clear();
@@ -77,6 +81,8 @@ class Hair {
     deinit();
     const int N = params_.b200.ncontrol_points;
     const std::int64_t S = scalp.nvertices;                                   // hair.cc:58
+    if (params_.b200.devices.size() > 1) { setup_group(scalp, S, N); return; }
+    if (params_.b200.devices.size() == 1) params_.b200.device = params_.b200.devices[0];
     if (!check(bh_create(&sim_, S, N, params_.b200.device), "bh_create")) { sim_ = nullptr; return; }
     // init_simulation (hair.cc:236-361): jitter on the host exactly as the reference, expansion on the device,
     // tangent plane on the host (libm + simplex noise), uploaded to plane 2.
@@ -118,6 +124,11 @@ class Hair {
       return;
     }
     if (!push_params()) return;                                               // uniforms are re-sent every frame (hair.cc:107-110)
+    if (group_) {
+      if (check(bh_group_step(group_, dt, params_.b200.substeps), "bh_group_step") && group_gl_)
+        check(bh_group_gather_to_gl(group_, 1u << BH_PLANE_POSITION), "bh_group_gather_to_gl");   // the render VAO reads positions (hair.cc:371-389)
+      return;
+    }
     check(bh_step(sim_, dt, params_.b200.substeps), "bh_step");
   }
 
@@ -136,22 +147,43 @@ class Hair {
   const std::vector<std::int32_t>& patch_indices() const noexcept { return patch_indices_; }   // mesh_.ibo contents, nelems = size()
 
   /* Zero-copy: step straight into the GL buffer the render VAO is bound to (needs a current GL context). */
-  bool register_gl_buffer(unsigned int gl_buffer) { return sim_ && check(bh_register_gl_buffer(sim_, gl_buffer), "bh_register_gl_buffer"); }
-  bool unregister_gl_buffer() { return sim_ && check(bh_unregister_gl_buffer(sim_), "bh_unregister_gl_buffer"); }
-  /* Copy path: planes to host memory (NULL = skip), V float4 each. */
-  bool download(float* pos4, float* vel4, float* tan4) { return sim_ && check(bh_download(sim_, pos4, vel4, tan4), "bh_download"); }
+  bool register_gl_buffer(unsigned int gl_buffer) {
+    if (group_) {                                                             // sharded: the GL buffer of the render GPU is the gather target
+      group_gl_ = check(bh_group_register_gl_buffer(group_, gl_buffer, params_.b200.devices[0]), "bh_group_register_gl_buffer") &&
+                  check(bh_group_gather_to_gl(group_, 7u), "bh_group_gather_to_gl");          // all three planes once; positions after every update
+      return group_gl_;
+    }
+    return sim_ && check(bh_register_gl_buffer(sim_, gl_buffer), "bh_register_gl_buffer");
+  }
+  bool unregister_gl_buffer() {
+    if (group_) { group_gl_ = false; return check(bh_group_unregister_gl_buffer(group_), "bh_group_unregister_gl_buffer"); }
+    return sim_ && check(bh_unregister_gl_buffer(sim_), "bh_unregister_gl_buffer");
+  }
+  /* Copy path: planes to host memory (NULL = skip), V float4 each, global strand order whatever the sharding. */
+  bool download(float* pos4, float* vel4, float* tan4) {
+    if (group_) return check(bh_group_download(group_, pos4, vel4, tan4), "bh_group_download");
+    return sim_ && check(bh_download(sim_, pos4, vel4, tan4), "bh_download");
+  }
+  /* Sharded setups: the position plane of the whole scalp on the render GPU (devices[0]), gathered by peer copies. */
+  void* gather_positions(float* ms = nullptr) {
+    void* ptr = nullptr;
+    if (!group_ || !check(bh_group_gather_plane(group_, BH_PLANE_POSITION, params_.b200.devices[0], &ptr, ms), "bh_group_gather_plane")) return nullptr;
+    return ptr;
+  }
 
   /* The tess-stream half of Hair::render (hair.cc:141-173): the interpolated render strands as the GL_LINES vertex stream
    * (xyz, relPos; two float4 per sub-segment) that the reference captures by transform feedback and draws with
    * glDrawTransformFeedback, for params().tess. Returns the number of float4 (0 on failure); they stay on the device
    * (bh_tess_device_buffer) and are also copied to `out4_host` when it is not null (room for stream_count() float4). */
   std::int64_t stream_count() {
+    if (group_) { log_error("Hair::stream: not available on a sharded setup (gather the planes to one device first)."); return 0; }
     if (!ensure_patches()) return 0;
     const bh_tess_params t = tess_params();
     const std::int64_t n = bh_tess_stream_count(sim_, &t);
     return n > 0 ? n : 0;
   }
   std::int64_t stream(float* out4_host = nullptr) {
+    if (group_) { log_error("Hair::stream: not available on a sharded setup (gather the planes to one device first)."); return 0; }
     if (!ensure_patches()) return 0;
     const bh_tess_params t = tess_params();
     if (!check(bh_tess_stream(sim_, &t, out4_host), "bh_tess_stream")) return 0;
@@ -163,16 +195,37 @@ class Hair {
   bool load_state(const char* path) { return sim_ && check(bh_load_state(sim_, path, nullptr), "bh_load_state"); }
 
   bh_sim* handle() noexcept { return sim_; }
+  bh_group* group_handle() noexcept { return group_; }
 
  private:
+  void setup_group(ScalpMesh const& scalp, std::int64_t S, int N) {
+    const std::vector<int>& devs = params_.b200.devices;
+    if (!check(bh_group_create(&group_, devs.data(), static_cast<int>(devs.size()), S, N), "bh_group_create")) { group_ = nullptr; return; }
+    std::vector<float> rv(static_cast<size_t>(S));
+    std::vector<float> tan(static_cast<size_t>(S) * N * 4);
+    bool ok = check(bh_random_values(params_.b200.seed, 0, S, rv.data()), "bh_random_values") &&
+              check(bh_group_init_strands(group_, scalp.positions, scalp.normals, rv.data(), params_.sim.maxlength), "bh_group_init_strands") &&
+              check(bh_init_tangents_host(scalp.normals, S, 0, S, N, params_.sim.maxlength, tan.data()), "bh_init_tangents_host") &&
+              check(bh_group_upload(group_, nullptr, nullptr, tan.data()), "bh_group_upload(tangents)");
+    if (ok && scalp.indices && scalp.nfaces > 0 && N > 1) {
+      patch_indices_.resize(static_cast<size_t>(6) * scalp.nfaces * (N - 1));
+      ok = check(bh_build_patch_indices(scalp.indices, scalp.nfaces, N, patch_indices_.data(), devs[0]), "bh_build_patch_indices");
+    }
+    if (ok) ok = push_params();
+    if (!ok) { deinit(); return; }
+    nroots_ = static_cast<int>(S);
+    params_.readonly.nroots = nroots_;
+    params_.readonly.nControlPoints = N;
+  }
   bool push_params() {
     bh_params p;
-    if (!check(bh_get_params(sim_, &p), "bh_get_params")) return false;
+    if (!check(bh_get_params(group_ ? bh_group_shard(group_, 0) : sim_, &p), "bh_get_params")) return false;
     p.scale = params_.render.lengthScale;
     p.math = params_.b200.math;
     // The reference sends its boundingsphere_ member every frame even when no collider exists (latent UB:
     // hair.h:99 is uninitialised); here the shader default (0,0,0,1) (cs_simulation.glsl:43) stands until one is set.
     if (has_sphere_) for (int i = 0; i < 4; ++i) p.sphere[i] = boundingsphere_[i];
+    if (group_) return check(bh_group_set_params(group_, &p), "bh_group_set_params");
     return check(bh_set_params(sim_, &p), "bh_set_params");
   }
   bool ensure_patches() {                                                        // the element buffer of init_mesh, on the device
@@ -207,6 +260,8 @@ class Hair {
   Parameters_t params_;
   int nroots_ = 0;                         //< Number of strands / root vertices in the scalp.
   bh_sim* sim_ = nullptr;                  //< Replaces PingPongBuffer pbuffer_ + the cs_simulation program.
+  bh_group* group_ = nullptr;              //< ... or its sharded form (params().b200.devices.size() > 1); exactly one of the two is set.
+  bool group_gl_ = false;
   float boundingsphere_[4] = { 0.f, 0.f, 0.f, 1.f };
   bool has_sphere_ = false;
   std::vector<std::int32_t> patch_indices_;

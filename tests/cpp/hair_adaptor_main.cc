@@ -1,6 +1,6 @@
 // Drives barbu::Hair (include/barbu_hair.hpp) the way the reference's Renderer drives its Hair module
 // (core/renderer.cc:17-23,69-81; Application.cc:38-39): init, setup(scalp), per frame set_bounding_sphere + update(dt).
-// Usage: hair_adaptor_main <in.bin> <out.bin>
+// Usage: hair_adaptor_main <in.bin> <out.bin> [devices, e.g. 0,1 or 0,0 — sharded over those CUDA devices (bh_group_*)]
 //   in : int64 S, int64 F, int32 N, int32 nframes, uint32 seed, float dt, float scale, float sphere[4], int32 math,
 //        float pos[S*3], float nrm[S*3], int32 tri[F*3]
 //   out: int64 V, int64 nelems, float pos4[V*4], float vel4[V*4], float tan4[V*4], int32 patch[nelems],
@@ -9,13 +9,14 @@
 // Exit codes: 0 ok, 2 usage/io, 3 module not initialised after setup.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "../../include/barbu_hair.hpp"
 
 int main(int argc, char** argv) {
-  if (argc != 3) return 2;
+  if (argc != 3 && argc != 4) return 2;
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) return 2;
   std::int64_t S = 0, F = 0; std::int32_t N = 0, nframes = 0, math = 0; std::uint32_t seed = 0; float dt = 0, scale = 0, sphere[4];
@@ -40,6 +41,9 @@ int main(int argc, char** argv) {
   hair.params().b200.seed = seed;
   hair.params().b200.math = math;
   hair.params().render.lengthScale = scale;
+  if (argc == 4)
+    for (const char* c = argv[3]; *c;) { hair.params().b200.devices.push_back(static_cast<int>(std::strtol(c, const_cast<char**>(&c), 10))); if (*c == ',') ++c; }
+  const bool sharded = hair.params().b200.devices.size() > 1;
   barbu::ScalpMesh scalp;
   scalp.positions = pos.data(); scalp.normals = nrm.data(); scalp.nvertices = S; scalp.indices = tri.data(); scalp.nfaces = F;
   hair.setup(scalp);
@@ -53,9 +57,13 @@ int main(int argc, char** argv) {
   if (!hair.download(p4.data(), v4.data(), t4.data())) return 3;
   const std::int64_t nelems = static_cast<std::int64_t>(hair.patch_indices().size());
   // the render-side half: tess-stream, then state file round trip, then the stream again — identical
-  std::vector<float> stream4(4 * static_cast<size_t>(hair.stream_count())), stream4b(stream4.size());
-  const std::int64_t nstream = hair.stream(stream4.data());
-  {
+  if (sharded) {                                     // the gathered position plane on the render GPU must be the downloaded one
+    float ms = -1.f;
+    if (!hair.gather_positions(&ms) || ms < 0.f) return 3;
+  }
+  std::vector<float> stream4(sharded ? 0 : 4 * static_cast<size_t>(hair.stream_count())), stream4b(stream4.size());
+  const std::int64_t nstream = sharded ? 0 : hair.stream(stream4.data());
+  if (!sharded) {
     const std::string state = std::string(argv[2]) + ".state";
     if (!hair.save_state(state.c_str()) || !hair.load_state(state.c_str())) return 3;
     std::remove(state.c_str());

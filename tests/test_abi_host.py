@@ -93,6 +93,8 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.bh_step(None, 0.01, 1) == hair.BH_ERR_INVALID
     assert lib.bh_random_values(1, -1, 4, None) == hair.BH_ERR_INVALID
     assert lib.bh_sphere_scalp_triangles(0, 4, None) == hair.BH_ERR_INVALID
+    assert b"bh_sphere_scalp_triangles" in lib.bh_last_error()           # host-only entry points report through bh_last_error too
+    assert lib.bh_step(None, 0.01, 1) == hair.BH_ERR_INVALID
     assert b"NULL" in lib.bh_last_error() or b"sim" in lib.bh_last_error()
     tri = np.array([[0, 1, 2]], np.int32)
     big = np.array([[0, 1, 2 ** 30]], np.int32)

@@ -12,7 +12,7 @@ from oracle import pyoracle as po
 from tests.util import DT, SPHERE, assert_bit_equal, sphere_state
 
 
-def run_driver(root_pos, root_nrm, tri, N, nframes, seed, dt, scale, sphere, math=0):
+def run_driver(root_pos, root_nrm, tri, N, nframes, seed, dt, scale, sphere, math=0, devices=None):
     exe = _build.build_cpp_adaptor_driver()
     S, F = root_pos.shape[0], tri.shape[0]
     with tempfile.TemporaryDirectory() as d:
@@ -22,7 +22,7 @@ def run_driver(root_pos, root_nrm, tri, N, nframes, seed, dt, scale, sphere, mat
             f.write(np.ascontiguousarray(root_pos, np.float32).tobytes())
             f.write(np.ascontiguousarray(root_nrm, np.float32).tobytes())
             f.write(np.ascontiguousarray(tri, np.int32).tobytes())
-        res = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=300)
+        res = subprocess.run([exe, fin, fout] + ([devices] if devices else []), capture_output=True, text=True, timeout=300)
         if res.returncode != 0:
             return res, None
         raw = open(fout, "rb").read()
@@ -69,3 +69,27 @@ def test_adaptor_matches_oracle_bit_exact(N, scale, nframes):
     assert_bit_equal(patch, po.patch_indices(tri, N), "patch indices")
     # Hair::stream() = the tess-stream half of the reference's render(), default tessellation 3 x 2 x 16, seed = params.b200.seed
     assert_bit_equal(stream, po.tess_stream(pos, gt, patch, N, scale, 3, 2, 16, 1234), "tess-stream")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0", "0,1"])
+def test_sharded_adaptor_matches_single_device_run(devices):
+    """params().b200.devices: the same scalp sharded over several devices behind the same Hair interface (bh_group_*, one host
+    thread) — positions, velocities, tangents and patch indices equal the oracle's single run bit for bit; the gathered
+    position plane exists on the render GPU. "0,0": two shards on one GPU; "0,1": two GPUs (skipped on a one-GPU box)."""
+    import torch
+    if len(set(devices.split(","))) > torch.cuda.device_count():
+        pytest.skip("needs more GPUs than this box has")
+    rows, cols, N, nframes = 15, 31, 16, 4                                # 465 strands: ragged shards
+    root_pos, root_nrm, tri, rv, pos, vel = sphere_state(rows, cols, N)
+    S = rows * cols
+    res, out = run_driver(root_pos, root_nrm, tri, N, nframes, 1234, float(DT), 1.45, SPHERE, devices=devices)
+    assert res.returncode == 0, res.stderr
+    gp, gv, gt, patch, stream = out
+    par = po.default_params(dt=float(DT), scale=1.45, sphere=SPHERE)
+    for _ in range(nframes):
+        po.step(pos, vel, S, N, par)
+    assert_bit_equal(gp, pos, "positions")
+    assert_bit_equal(gv, vel, "velocities")
+    assert_bit_equal(gt, po.init_tangents(root_nrm, N), "tangent plane")
+    assert_bit_equal(patch, po.patch_indices(tri, N), "patch indices")
