@@ -126,6 +126,8 @@ int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
   if (!s) return fail(BH_ERR_INVALID, "bh_create: out of host memory");
   s->device = device; s->nstrands = nstrands; s->nverts = nverts; s->nvertices = nstrands * (int64_t)nverts;
   bh_default_params(&s->params);
+  static const bool fuse_env = [] { const char* e = getenv("BH_SUBSTEP_FUSION"); return e && e[0] == '1'; }();   // tuning knob: default of bh_set_substep_fusion
+  s->fuse_substeps = fuse_env;
   cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&s->tile_counters, sizeof(unsigned int) * 32 * (kHostPipeStreams + 1));
   if (e == cudaSuccess) {
@@ -338,6 +340,16 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
   static const bool zigzag = [] { const char* e = getenv("BH_NO_ZIGZAG"); return !(e && e[0] == '1'); }();
+  if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+    // Frame-level fusion: the substeps of this frame as the passes of ONE launch (StepArgs::passes). Same arithmetic, same
+    // order per strand, so the result is bit-identical to `substeps` launches; HBM sees the state once per frame.
+    a.passes = substeps;
+    a.reverse = zigzag ? (int)(s->step_launches & 1) : 0;
+    BH_CUDA(bh::launch_step(a, s->params.math, s->stream, s->tile_counters + 32 * kHostPipeStreams));
+    s->launches += 1;
+    s->step_launches += 1;
+    return unmap_gl(s);
+  }
   for (int q = 0; q < substeps; ++q) {
     // Consecutive launches walk the shard in opposite directions: a launch starts with the tiles the previous one wrote
     // last, which are still in the 126 MB L2 — those reads, and the write-backs they replace, never reach HBM.
@@ -347,6 +359,12 @@ int bh_step(bh_sim* s, float dt, int substeps) {
     s->step_launches += 1;
   }
   return unmap_gl(s);
+}
+
+int bh_set_substep_fusion(bh_sim* s, int enabled) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_set_substep_fusion: sim is NULL");
+  s->fuse_substeps = enabled != 0;
+  return BH_OK;
 }
 
 int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {

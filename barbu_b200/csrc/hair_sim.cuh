@@ -45,6 +45,7 @@ struct bh_sim {
   cudaStream_t pipe[bh::kHostPipeStreams] = { nullptr, nullptr, nullptr, nullptr };
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
+  bool fuse_substeps = false;            // bh_set_substep_fusion: the substeps of a bh_step as passes of one launch
   int64_t launches = 0;
   int64_t step_launches = 0;             // launches of bh_step alone: parity = tile direction of the next one
   std::vector<cudaEvent_t> host_events;  // bh_step_host: two per slice + one, created on first use

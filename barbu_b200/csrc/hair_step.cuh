@@ -26,6 +26,13 @@ struct StepArgs {
   int ncaps;
   int reverse;            // streaming kernel: hand the tiles out from the last one down (see bh_step: alternates per launch)
   int tip_step;           // streaming kernel: step of a root chunk at which the tip of the previous strand leaves the pipeline
+  // Streaming kernel, frame-level fusion: `passes` > 1 runs that many consecutive steps (the substeps of a frame, same dt) in
+  // ONE launch. A warp takes `group_tiles` tiles at a time through all passes before it asks for the next group, so a pass
+  // re-reads what the previous one stored while it is still in L2: HBM sees 64 B per vertex per LAUNCH instead of per step.
+  // group_tiles * chunks-per-strand >= 4 (launcher): the store of a chunk is then always at least one bulk group older
+  // than the load of the same chunk for the next pass (the tile ring prefetches two chunks ahead).
+  int passes;
+  int group_tiles;
   Capsule caps[kMaxCapsules];
   // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
   // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.
@@ -48,6 +55,8 @@ int step_kernel_kind(const StepArgs& a);
 
 // hair_stream.cu
 bool stream_kernel_eligible(const StepArgs& a);
+// Whether `passes` consecutive steps of this shape can run as one fused launch of the streaming kernel (see StepArgs::passes).
+bool stream_fusion_eligible(const StepArgs& a, int passes);
 cudaError_t selftest_inversesqrt(unsigned long long* mismatches);
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 

@@ -85,6 +85,8 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, int c0, i
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups but the most recent one are COMPLETE (their global writes performed), not merely read out of shared memory
+__device__ __forceinline__ void tma_wait_complete_but1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- packed pairs ------------------------------------------------------------------------------
@@ -471,7 +473,9 @@ __device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pi
 
 // NS = 8: a tensor row is one strand of nverts % 8 == 0 vertices. NS = 4: nverts == 4 and a row is TWO consecutive strands
 // (the same 128 bytes), so every chunk is a whole row with roots in slots 0 and 4; a.nstrands is even (launcher).
-template <class PM, bool ORIGIN, int NS, bool CAPS>
+// FUSED: the launch runs StepArgs::passes steps over groups of tiles (frame-level substep fusion); its own instantiation, so
+// that the plain one-step launch keeps its code (and registers) exactly.
+template <class PM, bool ORIGIN, int NS, bool CAPS, bool FUSED>
 #ifndef BH_STREAM_MINB
 #define BH_STREAM_MINB 3
 #endif
@@ -494,6 +498,11 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   const int chunks = NS == 8 ? (a.nverts + kK - 1) / kK : 1;                // per row; the last one may be ragged (see tip_step)
   const long long nrows = NS == 8 ? a.nstrands : a.nstrands / 2;
   const unsigned int ntiles = (unsigned int)((nrows + 31) / 32);
+  // Work is handed out in GROUPS of tiles; a warp streams a group `passes` times (pass after pass, tile after tile, chunk
+  // after chunk) before it takes the next. passes == 1: a group is one tile and this is the plain one-step launch. The last
+  // group absorbs the remainder, so every group has at least group_tiles tiles.
+  const int passes = FUSED ? a.passes : 1, gtiles = FUSED ? a.group_tiles : 1;
+  const unsigned int ngroups = FUSED ? ntiles / (unsigned int)gtiles : ntiles;
 
   if (lane == 0) {
     mbar_init(bar_s, 1);
@@ -502,20 +511,28 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   }
   __syncwarp();
 
-  auto grab = [&]() -> int {                                                // next tile of this warp, -1 when none is left
+  auto grab = [&]() -> int {                                                // next group of this warp, -1 when none is left
     unsigned int t = 0;
     if (lane == 0) t = atomicAdd(tile_counter, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= ntiles) return -1;
-    return (int)(a.reverse ? ntiles - 1u - t : t);                            // strands are independent: any tile order is the same result
+    if (t >= ngroups) return -1;
+    return (int)(a.reverse ? ngroups - 1u - t : t);                           // strands are independent: any order is the same result
   };
-  auto issue_load = [&](int tile, int c, int b) {                           // lane 0 only
+  // A stream position is (absolute tile, meta) with meta = chunk | tile-in-group << 16 | pass << 24: advanced without divisions.
+  const int lastbase = (int)((ngroups - 1u) * (unsigned int)gtiles);         // first tile of the last group (which absorbs the remainder)
+  auto chunk_of = [&](int meta) -> int { return FUSED ? meta & 0xffff : meta; };
+  auto issue_load = [&](int tile, int meta, int b) {                        // lane 0 only
+    const int c = chunk_of(meta);
     const uint32_t bar = bar_s + 8 * b, dst = tiles_s + b * kStageBytes;
+    // a chunk of a later pass is what this warp stored one pass ago: that store is at least one bulk group older than the most
+    // recent one (StepArgs::group_tiles), and it must have been performed, not just read out of shared memory
+    if (FUSED && (meta >> 24) != 0) tma_wait_complete_but1();
     mbar_expect_tx(bar, kStageBytes);
     tma_load_tile(dst, &mapP, c * 32, tile * 32, bar);
     tma_load_tile(dst + kPlaneTile, &mapV, c * 32, tile * 32, bar);
   };
-  auto issue_store = [&](int tile, int c, int b) {                          // lane 0 only
+  auto issue_store = [&](int tile, int meta, int b) {                       // lane 0 only
+    const int c = chunk_of(meta);
     const uint32_t src = tiles_s + b * kStageBytes;
     tma_store_tile(&mapP, c * 32, tile * 32, src);
     tma_store_tile(&mapV, c * 32, tile * 32, src + kPlaneTile);
@@ -532,9 +549,19 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   };
   int tC = grab(), cC = 0;
   if (tC < 0) { leave(); return; }
-  auto next_pos = [&](int& t, int& c) {
+  if (FUSED) tC *= gtiles;
+  auto next_pos = [&](int& t, int& c) {                                     // t: tile, c: chunk (FUSED: meta)
     if (t < 0) return;
-    if (++c == chunks) { c = 0; t = grab(); }
+    if (!FUSED) { if (++c == chunks) { c = 0; t = grab(); } return; }
+    if ((c & 0xffff) + 1 < chunks) { c += 1; return; }                      // next chunk of the tile
+    c &= ~0xffff;
+    const int ti = (c >> 16) & 0xff, gbase = t - ti;
+    const int gcount = gbase == lastbase ? (int)ntiles - gbase : gtiles;
+    if (ti + 1 < gcount) { c += 1 << 16; t += 1; return; }                  // next tile of the group
+    const int p = c >> 24;
+    if (p + 1 < passes) { c = (p + 1) << 24; t = gbase; return; }           // next pass over the group
+    const int g = grab();                                                   // next group
+    t = g < 0 ? -1 : g * gtiles; c = 0;
   };
   int tN = tC, cN = cC; next_pos(tN, cN);
   int tL = tN, cL = cN; next_pos(tL, cL);
@@ -567,7 +594,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     if (live) mbar_wait(bar_s + 8 * b, (q >> 1) & 1);
     float4* bP = reinterpret_cast<float4*>(tiles + b * kStageBytes) + lane * 8;
     float4* bV = bP + kPlaneTile / 16;
-    const bool root_chunk = !live || cC == 0;
+    const bool root_chunk = !live || chunk_of(cC) == 0;
     if (NS == 4) stream_chunk<PM, ORIGIN, 4, CAPS>(a, nz, s, sep, 0x11u, bP, bV, myR, sw);
     // capsule variant, exact profile: one step body for both kinds of chunk (its extra tests already crowd the instruction
     // cache: with two bodies the "arms" scene of tests/reports/config3.py runs at 6.7 ms per launch instead of 5.1); the
@@ -633,7 +660,7 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
             CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
-struct DeviceInfo { int sms = 0; bool ready[12] = {}; int blocks_per_sm[12] = {}; };
+struct DeviceInfo { int sms = 0; bool ready[24] = {}; int blocks_per_sm[24] = {}; };
 
 // Bounding sphere of capsule k for caps_may_touch(): centre = midpoint of the axis, radius = half axis + capsule radius,
 // widened by 1e-3 relative + 1e-6 absolute — orders of magnitude above the fp32 rounding of either the bound or the exact
@@ -661,8 +688,14 @@ void fill_capsule_bounds(StepArgs& b) {
   }
 }
 
-template <class PM, bool ORIGIN, int NS, bool CAPS = false>
-cudaError_t launch_stream_t(const StepArgs& a_in, cudaStream_t stream, unsigned int* tile_counter, int variant) {
+// Tiles per group of a fused launch: the smallest count with group_tiles * chunks >= 4 (see StepArgs::group_tiles).
+int fusion_group_tiles(int nverts) {
+  const int chunks = nverts == 4 ? 1 : (nverts + kK - 1) / kK;
+  return chunks >= 4 ? 1 : (4 + chunks - 1) / chunks;
+}
+
+template <class PM, bool ORIGIN, int NS, bool CAPS, bool FUSED>
+cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned int* tile_counter, int variant) {
   StepArgs a = a_in;
   a.tip_step = a.nverts % kK == 0 ? kK - 1 : a.nverts % kK - 1;
   if (CAPS) fill_capsule_bounds(a);
@@ -672,7 +705,7 @@ cudaError_t launch_stream_t(const StepArgs& a_in, cudaStream_t stream, unsigned 
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS, CAPS>;
+  auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS, CAPS, FUSED>;
   {
     std::lock_guard<std::mutex> g(mu);
     DeviceInfo& di = info[dev];
@@ -707,7 +740,11 @@ cudaError_t launch_stream_t(const StepArgs& a_in, cudaStream_t stream, unsigned 
     mapP = hit->mapP; mapV = hit->mapV;
   }
   const long long ntiles = ((NS == 8 ? a.nstrands : a.nstrands / 2) + 31) / 32;
-  long long blocks = (ntiles + kWarps - 1) / kWarps;
+  if (a.passes < 1) a.passes = 1;
+  a.group_tiles = a.passes > 1 ? fusion_group_tiles(a.nverts) : 1;
+  if (a.passes > 1 && ntiles < a.group_tiles) return cudaErrorInvalidValue;   // callers ask stream_fusion_eligible() first
+  const long long ngroups = ntiles / a.group_tiles;
+  long long blocks = (ngroups + kWarps - 1) / kWarps;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
   int per_sm = info[dev].blocks_per_sm[variant];
   if (occ_cap > 0 && occ_cap < per_sm) per_sm = occ_cap;
@@ -758,6 +795,20 @@ bool stream_kernel_eligible(const StepArgs& a) {
   const bool shape_ok = a.nverts == 4 ? a.nstrands >= 2 : (a.nverts >= 2 && (ragged_ok || a.nverts % kK == 0));
   return !disabled && a.iterations == kK && a.ncaps >= 0 && a.ncaps <= kMaxCapsules && shape_ok &&
          a.nstrands <= 0x7fffffffLL && a.r2 <= 1.8446744073709551616e19f && encode_tiled() != nullptr;
+}
+
+template <class PM, bool ORIGIN, int NS, bool CAPS = false>
+cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int* tile_counter, int variant) {
+  return a.passes > 1 ? launch_stream_tf<PM, ORIGIN, NS, CAPS, true>(a, stream, tile_counter, variant + 12)
+                      : launch_stream_tf<PM, ORIGIN, NS, CAPS, false>(a, stream, tile_counter, variant);
+}
+
+bool stream_fusion_eligible(const StepArgs& a, int passes) {
+  static const bool disabled = [] { const char* e = getenv("BH_NO_SUBSTEP_FUSION"); return e && e[0] == '1'; }();   // tuning knob
+  if (disabled || passes < 2 || passes > 64 || !stream_kernel_eligible(a)) return false;   // the pass counter shares a word with the chunk index
+  if (a.nverts == 4 && a.nstrands % 2) return false;                        // the odd last strand runs on the per-strand kernel: step by step
+  const long long ntiles = ((a.nverts == 4 ? a.nstrands / 2 : a.nstrands) + 31) / 32;
+  return ntiles >= fusion_group_tiles(a.nverts);
 }
 
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {

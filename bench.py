@@ -306,10 +306,12 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(math_id, sampler):
+    def timed_region(math_id, sampler, fused=False):
         """W untimed steps (+ pre-roll so clocks settle), then exactly K steps between two CUDA events on the launching
-        stream, barrier + synchronize on both sides, max over ranks. Returns (ms_total, launches)."""
+        stream, barrier + synchronize on both sides, max over ranks. Returns (ms_total, launches).
+        fused: the 4 substeps of a frame as 4 passes of ONE launch (bh_set_substep_fusion) — reported as value_fused."""
         sim.configure(math=math_id)
+        sim.set_substep_fusion(fused or args.fused_main)
         sim.init_sphere_scalp(ROWS, cols_total, first, rv, order=order)   # every profile starts from the same cold state
         for i in range(args.settle):
             sim.step(DT, SUBSTEPS)
@@ -358,7 +360,7 @@ def run_gpu(args, rank, world, local_rank):
                          "value": world * V * SUBSTEPS * n / (float(sms.item()) * 1e-3), "unit": UNIT}
         if sampler is not None:
             sampler.mark_end()
-        sustained_by_math[math_id] = sustained
+        sustained_by_math[(math_id, fused)] = sustained
         return max(per_rank), launches
 
     # ---- device-resident timing: value + roofline ---------------------------------------------------
@@ -373,14 +375,23 @@ def run_gpu(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     # the other arithmetic profile, same workload and timing rules (reported beside the headline, never instead of it)
     other = None
+    other_math = bb.BH_MATH_EXACT if math == bb.BH_MATH_FAST else bb.BH_MATH_FAST
     if not args.no_other_profile:
-        other_math = bb.BH_MATH_EXACT if math == bb.BH_MATH_FAST else bb.BH_MATH_FAST
         sampler2 = ClockSampler(local_rank)
         if rank == 0:
             sampler2.start()
         ms2, launches2 = timed_region(other_math, sampler2 if rank == 0 else None)
         clocks2 = sampler2.stop() if rank == 0 else None
         other = (ms2, launches2, clocks2)
+        sim.configure(math=math)
+
+    # ---- the same frames with the substeps fused into one launch per frame (tiles stay in L2 between substeps) -----------
+    fused = {}
+    if not args.no_fused:
+        for m_id, name in ((math, args.math),) + (() if args.no_other_profile else ((other_math, "exact" if args.math == "fast" else "fast"),)):
+            msf, lf = timed_region(m_id, None, fused=True)
+            fused[name] = (msf, lf, sustained_by_math.get((m_id, True)))
+        sim.set_substep_fusion(False)
         sim.configure(math=math)
 
     # ---- end to end through the C ABI with HOST buffers (bh_step_host): H2D + 4 substeps + D2H per step ---
@@ -485,8 +496,8 @@ def run_gpu(args, rank, world, local_rank):
         line["roofline"]["traffic"] = traffic.get(args.math)
         line["roofline"]["traffic_source"] = ("profiles/traffic_bytes_per_launch.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                               "`ncu --set full` capture of this launch shape; static, not measured in this run)") if traffic.get(args.math) else None
-        if sustained_by_math.get(math) is not None:
-            line["sustained"] = dict(sustained_by_math[math], note="the timed loop continued for >= --sustain seconds, same events and rules")
+        if sustained_by_math.get((math, False)) is not None:
+            line["sustained"] = dict(sustained_by_math[(math, False)], note="the timed loop continued for >= --sustain seconds, same events and rules")
         if args.emulate_world > 0:
             line["emulated_shard"] = {"rank": erank, "world": eworld, "order": args.order}
         if other is not None:
@@ -496,11 +507,24 @@ def run_gpu(args, rank, world, local_rank):
             ach2 = BYTES_PER_VERTEX_PER_LAUNCH * V / per2 / 1e9
             line["other_profile"] = {"math": name2, "value": world * V * SUBSTEPS * args.steps / (ms2 * 1e-3), "unit": UNIT,
                                      "ms_per_step": ms2 / args.steps, "gpu_launches": launches2, "clocks": clocks2,
-                                     "sustained": sustained_by_math.get(other_math),
+                                     "sustained": sustained_by_math.get((other_math, False)),
                                      "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
                                                   "traffic": traffic.get(name2), "ms_per_launch": per2 * 1e3},
                                      "note": "same workload, steps and timing rules; exact = bit-identical to the CPU oracle, "
                                              "fast = FMA-contracted + MUFU.RSQ arithmetic (<= 1e-5 relative per vertex after one step)"}
+        def fused_obj(name):
+            msf, lf, sus = fused[name]
+            return {"value": world * V * SUBSTEPS * args.steps / (msf * 1e-3), "unit": UNIT, "ms_per_step": msf / args.steps, "gpu_launches": lf,
+                    "substeps_per_launch": SUBSTEPS, "hbm_algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V,
+                    "hbm_achieved_gbs_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V / (msf * 1e-3 / max(lf, 1)) / 1e9,
+                    "sustained": sus,
+                    "note": "bh_set_substep_fusion(1): the 4 substeps of a frame as 4 passes of ONE launch, a warp re-reading from L2 what its "
+                            "previous pass stored; bit-identical to 4 launches (tests). HBM traffic is 64 B per vertex per LAUNCH, so this "
+                            "figure is updates/s only — `roofline` above stays the unfused, HBM-bound launch (SURVEY.md 8d accounting)"}
+        if args.math in fused:
+            line["value_fused"] = fused_obj(args.math)
+        if other is not None and line["other_profile"]["math"] in fused:
+            line["other_profile"]["value_fused"] = fused_obj(line["other_profile"]["math"])
         if gather is not None:
             line["allgather"] = gather
         emit(json.dumps(line))
@@ -575,6 +599,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-other-profile", action="store_true", help="time only the --math profile")
+    ap.add_argument("--fused-main", action="store_true", help="profiling runs: the main timed region itself uses fused substeps")
+    ap.add_argument("--no-fused", action="store_true", help="skip the fused-substeps legs (value_fused)")
     ap.add_argument("--allgather", action="store_true", help="N > 1: also time the optional NCCL all-gather of the position plane")
     ap.add_argument("--preroll", type=float, default=0.0, help="minimum seconds of untimed warm-up (0 for profiler runs)")
     ap.add_argument("--settle", type=int, default=100,

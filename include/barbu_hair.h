@@ -128,6 +128,13 @@ int  bh_build_patch_indices(const int32_t* tri_indices, int64_t nfaces, int nver
 /* ---- Hair::update(dt) (hair.cc:89-125) ------------------------------------------------------- */
 /* `substeps` launches of the fused step kernel, each with dt/substeps (substeps = 1: reference). */
 int  bh_step(bh_sim* sim, float dt, int substeps);
+/* Frame-level substep fusion (off by default = one launch per substep, the reference's one dispatch per step). When on,
+ * bh_step(dt, substeps > 1) runs the substeps of the frame as consecutive PASSES of one launch of the streaming kernel: a warp
+ * takes a group of tiles through all passes before it asks for more, so a pass re-reads from L2 what the previous one
+ * stored, and HBM carries 64 B per vertex per frame instead of per substep. Per strand the operations and their order are
+ * those of `substeps` separate launches: results are bit-identical. Shapes the streaming kernel does not take (nverts = 1,
+ * iteration counts other than 8, fewer tiles than one group) silently keep one launch per substep. */
+int  bh_set_substep_fusion(bh_sim* sim, int enabled);
 /* Same through HOST buffers: upload pos/vel, step, download pos/vel; copies are chunked and
  * overlapped with the kernels on internal streams. Buffers should be page-locked (bh_host_alloc). */
 int  bh_step_host(bh_sim* sim, float dt, int substeps, float* pos4, float* vel4);

@@ -731,3 +731,80 @@ def test_random_states_bit_exact(N, seed):
     gp, gv = gpu_steps(pos, vel, S, N, 6, dt=dt, scale=scale, sphere=sphere)
     assert_bit_equal(gp, rp, "positions")
     assert_bit_equal(gv, rv, "velocities")
+
+
+# ---- frame-level substep fusion: k substeps as k passes of one launch ------------------------------------------------------
+
+@pytest.mark.parametrize("S,N,k", [(4096, 32, 4), (4000, 32, 2), (1000, 8, 4), (2048 + 77, 16, 3), (33333, 4, 4), (7001, 20, 4), (300, 128, 2),
+                                   (96, 8, 4), (40, 8, 4), (65, 4, 2)])
+@pytest.mark.parametrize("math", [bb.BH_MATH_EXACT, bb.BH_MATH_FAST])
+def test_fused_substeps_bit_identical_to_separate_launches(S, N, k, math):
+    """bh_set_substep_fusion: bh_step(dt, k) as k passes of ONE launch must equal k launches bit for bit in BOTH arithmetic
+    profiles (same operations per strand, only the schedule differs) — whole tiles and ragged ones, every chunk count
+    (group sizes 1, 2 and 4 tiles), the two-strands-per-row shape (N = 4), shapes too small for a group (silent fallback) —
+    and the exact profile must still equal the oracle."""
+    pos, vel = ragged_state(S, N)
+    outs = []
+    for fuse in (False, True):
+        with bb.HairSim(S, N) as sim:
+            sim.configure(scale=1.45, sphere=SPHERE, math=math)
+            sim.set_substep_fusion(fuse)
+            sim.upload(pos, vel)
+            l0 = sim.launch_count
+            for _ in range(3):
+                sim.step(float(DT), k)
+            launches = sim.launch_count - l0
+            outs.append(sim.download()[:2] + (launches,))
+    assert_bit_equal(outs[1][0], outs[0][0], "positions, fused vs separate launches")
+    assert_bit_equal(outs[1][1], outs[0][1], "velocities, fused vs separate launches")
+    ntiles = ((S // 2 if N == 4 else S) + 31) // 32
+    chunks = 1 if N == 4 else (N + 7) // 8
+    group = 1 if chunks >= 4 else -(-4 // chunks)
+    fusable = ntiles >= group and not (N == 4 and S % 2)
+    assert outs[0][2] >= 3 * k and outs[1][2] == (3 if fusable else outs[0][2]), (outs[0][2], outs[1][2])
+    if math == bb.BH_MATH_EXACT:
+        h = float(np.float32(DT) / np.float32(k))
+        par = po.default_params(dt=h, scale=1.45, sphere=SPHERE)
+        for _ in range(3 * k):
+            po.step(pos, vel, S, N, par, nthreads=8)
+        assert_bit_equal(outs[1][0], pos, "fused positions vs the oracle")
+        assert_bit_equal(outs[1][1], vel, "fused velocities vs the oracle")
+
+
+def test_fused_substeps_full_size_bit_identical_and_capsules():
+    """configs[1] at full size (2^20 x 32, 4 substeps): fused frames == unfused frames over all 33.5M vertices, settled
+    state with contacts; and a capsule scene at 2^16 x 32."""
+    rows, cols, N = 1024, 1024, 32
+    S = rows * cols
+    res = []
+    for fuse in (False, True):
+        with bb.HairSim(S, N) as sim:
+            sim.configure(scale=1.45, sphere=SPHERE, math=bb.BH_MATH_EXACT)
+            sim.set_substep_fusion(fuse)
+            sim.init_sphere_scalp(rows, cols, 0, bb.random_values(1234, 0, S), order=bb.BH_SCALP_COLUMN_MAJOR)
+            for _ in range(12):
+                sim.step(float(DT), 4)
+            res.append(sim.checksum(3))
+            if fuse:
+                p1, v1, _ = sim.download()
+            else:
+                p0, v0, _ = sim.download()
+    assert_bit_equal(p1, p0, "positions"); assert_bit_equal(v1, v0, "velocities")
+    assert res[0] == res[1]
+    S, N = 1 << 16, 32
+    pos, vel = ragged_state(S, N)
+    cfg = bb.default_params(); cfg.scale = 1.45; cfg.math = bb.BH_MATH_EXACT
+    for i, x in enumerate(SPHERE): cfg.sphere[i] = x
+    caps = CAPSULE_SETS["arms"]
+    cfg.ncapsules = len(caps)
+    for q, (a, b, r) in enumerate(caps):
+        for i in range(3): cfg.capsules[q].a[i], cfg.capsules[q].b[i] = a[i], b[i]
+        cfg.capsules[q].radius = r
+    outs = []
+    for fuse in (False, True):
+        with bb.HairSim(S, N) as sim:
+            sim.set_params(cfg); sim.set_substep_fusion(fuse); sim.upload(pos, vel)
+            for _ in range(5):
+                sim.step(float(DT), 4)
+            outs.append(sim.download()[:2])
+    assert_bit_equal(outs[1][0], outs[0][0], "capsule scene positions"); assert_bit_equal(outs[1][1], outs[0][1], "capsule scene velocities")
