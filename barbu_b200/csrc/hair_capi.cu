@@ -411,8 +411,13 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(dV, vel4 + 4 * off, bytes, cudaMemcpyHostToDevice, up);
     if (e == cudaSuccess) e = cudaEventRecord(uploaded, up);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(run, uploaded, 0);
-    const bh::StepArgs a = make_args(s, h, dP, dV, count);
-    for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+    bh::StepArgs a = make_args(s, h, dP, dV, count);
+    if (e == cudaSuccess && s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+      a.passes = substeps;                                                  // the substeps of the slice as passes of one launch
+      e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1;
+    } else {
+      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+    }
     if (e == cudaSuccess) e = cudaEventRecord(stepped, run);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(down, stepped, 0);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, down);
@@ -424,9 +429,57 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
   return BH_OK;
 }
 
+int bh_step_readback(bh_sim* s, float dt, int substeps, float* pos4) {
+  if (!s || !pos4) return fail(BH_ERR_INVALID, "bh_step_readback: NULL argument");
+  if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_step_readback: no strand state (call bh_upload / bh_init_* first)");
+  if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step_readback: substeps < 1");
+  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_step_readback: buffer 0 is a GL buffer (the renderer reads it in place)");
+  DeviceGuard g(s->device);
+  const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
+  // The reference's frame: uniforms in, Hair::update, positions out (hair.cc:89-125 + the consumer of buffer 0). Strands are
+  // independent, so the shard is stepped slice by slice on one stream while the position plane of the slices already done
+  // leaves on another: the device->host copy (the long pole: 16 B per vertex over PCIe) starts after 1/nslices of the
+  // compute instead of after all of it, and the step of slice k+1 hides behind the copy of slice k.
+  const int64_t S = s->nstrands;
+  static const int nslices = [] { const char* e = getenv("BH_READBACK_SLICES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();   // tuning knob
+  int64_t slice = (S + nslices - 1) / nslices;
+  if (slice < 8192) slice = 8192;
+  slice = (slice + 127) / 128 * 128;                                        // whole 32-strand tiles, even strand counts
+  const int64_t count_slices = (S + slice - 1) / slice;
+  while ((int64_t)s->host_events.size() < 2 * count_slices + 1) {
+    cudaEvent_t ev;
+    BH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    s->host_events.push_back(ev);
+  }
+  cudaStream_t run = s->pipe[1], down = s->pipe[2];
+  cudaEvent_t ev0 = s->host_events[2 * count_slices];
+  cudaError_t e = cudaEventRecord(ev0, s->stream);                          // order after whatever is queued on the sim's stream
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(run, ev0, 0);
+  for (int64_t k = 0; k < count_slices && e == cudaSuccess; ++k) {
+    const int64_t first = k * slice, count = (first + slice <= S ? slice : S - first);
+    const size_t off = (size_t)first * s->nverts, bytes = (size_t)count * s->nverts * sizeof(float4);
+    float4* dP = s->planes[BH_PLANE_POSITION] + off;
+    bh::StepArgs a = make_args(s, h, dP, s->planes[BH_PLANE_VELOCITY] + off, count);
+    if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+      a.passes = substeps;
+      e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1;
+    } else {
+      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+    }
+    cudaEvent_t stepped = s->host_events[2 * k];
+    if (e == cudaSuccess) e = cudaEventRecord(stepped, run);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(down, stepped, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pos4 + 4 * off, dP, bytes, cudaMemcpyDeviceToHost, down);
+  }
+  for (int i = 1; i < 3; ++i) { cudaError_t e2 = cudaStreamSynchronize(s->pipe[i]); if (e == cudaSuccess) e = e2; }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "bh_step_readback", e); }
+  return BH_OK;
+}
+
 int bh_host_alloc(void** ptr, uint64_t nbytes) {
   if (!ptr) return fail(BH_ERR_INVALID, "bh_host_alloc: ptr is NULL");
-  BH_CUDA(cudaMallocHost(ptr, (size_t)nbytes));
+  // portable: page-locked for every CUDA context of the process (the shards of a bh_group live on several devices)
+  BH_CUDA(cudaHostAlloc(ptr, (size_t)nbytes, cudaHostAllocPortable));
   return BH_OK;
 }
 int bh_host_free(void* ptr) {

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
-    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_step_host", "bh_host_alloc",
+    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
@@ -117,6 +117,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_step": ([vp, f32, C.c_int], C.c_int),
         "bh_step_host": ([vp, f32, C.c_int, vp, vp], C.c_int),
         "bh_set_substep_fusion": ([vp, C.c_int], C.c_int),
+        "bh_step_readback": ([vp, f32, C.c_int, vp], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
@@ -401,6 +402,13 @@ class HairSim:
             if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != 4 * self.nvertices:
                 raise ValueError("host planes must be C-contiguous float32 with 4*V elements")
         _check(self._lib.bh_step_host(self._h, dt, substeps, _ptr(pos4), _ptr(vel4)))
+
+    def step_readback(self, dt: float, substeps: int, pos4: np.ndarray):
+        """Hair::update with the state resident on the device, then the position plane in `pos4` (bh_step_readback: the
+        device->host copy of a slice of strands overlaps the step of the next slice)."""
+        if pos4.dtype != np.float32 or not pos4.flags.c_contiguous or pos4.size != 4 * self.nvertices:
+            raise ValueError("pos4 must be C-contiguous float32 with 4*V elements")
+        _check(self._lib.bh_step_readback(self._h, dt, substeps, _ptr(pos4)))
 
     @property
     def launch_count(self) -> int:

@@ -422,8 +422,7 @@ def run_gpu(args, rank, world, local_rank):
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             sim.set_bounding_sphere(SPHERE)
-            sim.step(DT, SUBSTEPS)
-            sim.download_into(pos4=hp.array)
+            sim.step_readback(DT, SUBSTEPS, hp.array)           # returns after the position plane arrived
         torch.cuda.synchronize()
         t_res = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if dist is not None:
@@ -476,8 +475,8 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * V, "d2h_bytes_per_step": 32 * V,
                     "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)"},
             "e2e_resident_state": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 16 * V,
-                                   "steps": e2e_steps, "api": "bh_set_bounding_sphere + bh_step + bh_download(position plane): the "
-                                   "reference's Hair::update call pattern, state resident on the device, positions read back to pinned host memory"},
+                                   "steps": e2e_steps, "api": "bh_set_bounding_sphere + bh_step_readback(position plane): the reference's Hair::update "
+                                   "call pattern, state resident on the device, positions read back to pinned host memory slice by slice behind the steps"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -138,7 +138,12 @@ int  bh_set_substep_fusion(bh_sim* sim, int enabled);
 /* Same through HOST buffers: upload pos/vel, step, download pos/vel; copies are chunked and
  * overlapped with the kernels on internal streams. Buffers should be page-locked (bh_host_alloc). */
 int  bh_step_host(bh_sim* sim, float dt, int substeps, float* pos4, float* vel4);
-int  bh_host_alloc(void** ptr, uint64_t nbytes);     /* cudaMallocHost */
+/* The reference's own frame with the state resident on the device: Hair::update(dt) takes no buffers (hair.cc:89-125), the
+ * host sends uniforms (bh_set_bounding_sphere) and a host-side consumer reads the position plane of buffer 0. One call:
+ * `substeps` steps, then plane 0 (V float4) in pos4; the shard is stepped slice by slice and the device->host copy of a
+ * slice overlaps the step of the next. Returns when pos4 is complete. pos4 should be page-locked (bh_host_alloc). */
+int  bh_step_readback(bh_sim* sim, float dt, int substeps, float* pos4);
+int  bh_host_alloc(void** ptr, uint64_t nbytes);     /* cudaHostAlloc, portable across the devices of a group */
 int  bh_host_free(void* ptr);
 /* Kernel launches issued by this sim so far (bench.py's gpu_launches claim). */
 int64_t bh_launch_count(const bh_sim* sim);

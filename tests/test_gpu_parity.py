@@ -808,3 +808,31 @@ def test_fused_substeps_full_size_bit_identical_and_capsules():
                 sim.step(float(DT), 4)
             outs.append(sim.download()[:2])
     assert_bit_equal(outs[1][0], outs[0][0], "capsule scene positions"); assert_bit_equal(outs[1][1], outs[0][1], "capsule scene velocities")
+
+
+@pytest.mark.parametrize("S,N,k,fuse", [(20000, 16, 2, False), (70001, 20, 4, True), (33333, 4, 3, False), (5000, 32, 4, True), (1 << 17, 32, 4, True)])
+def test_step_readback_equals_step_then_download(S, N, k, fuse):
+    """bh_step_readback (the reference's frame: state resident, positions out; sliced so the copy overlaps the steps) ==
+    bh_step + bh_download, bit for bit, and the velocities left on the device agree too; also through bh_step_host."""
+    pos, vel = ragged_state(S, N)
+    with bb.HairSim(S, N) as a, bb.HairSim(S, N) as b:
+        for sim in (a, b):
+            sim.configure(scale=1.45, sphere=SPHERE)
+            sim.set_substep_fusion(fuse)
+            sim.upload(pos, vel)
+        out = bb.PinnedBuffer(4 * S * N)
+        for _ in range(3):
+            a.step(float(DT), k)
+            b.step_readback(float(DT), k, out.array)
+        wp, wv, _ = a.download()
+        assert_bit_equal(out.array.reshape(-1, 4), wp, "positions read back slice by slice")
+        gp, gv, _ = b.download()
+        assert_bit_equal(gp, wp); assert_bit_equal(gv, wv, "velocities left on the device")
+        hp, hv = pos.reshape(-1).copy(), vel.reshape(-1).copy()
+        for _ in range(3):
+            b.step_host(float(DT), k, hp, hv)
+        assert_bit_equal(hp.reshape(-1, 4), wp, "bh_step_host with the same fusion setting")
+        out.free()
+    with bb.HairSim(64, 8) as sim:
+        with pytest.raises(bb.BarbuHairError):
+            sim.step_readback(float(DT), 1, np.zeros(4 * 64 * 8, np.float32))     # no strand state
