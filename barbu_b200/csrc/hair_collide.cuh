@@ -74,12 +74,24 @@ __device__ __forceinline__ bool capsule_bound_hit(const float (&b)[4], V3 p) {
   const float dx = p.x - b[0], dy = p.y - b[1], dz = p.z - b[2];
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < b[3];
 }
+// The capsule-shaped bound of StepArgs::capt for one position: squared distance to the axis in fast arithmetic against the
+// widened radius — the scalar form of caps_tight_touch() in hair_stream.cu, operation for operation, so that a lane passes
+// here exactly when it made its warp pass there. Out of the warps that reach the exact chain only few LANES (and few of the
+// eight vertices in flight) are near a capsule: gating the IEEE divisions and square roots with this instead of the
+// bounding sphere keeps the chain to the vertices that are about to be pushed out.
+__device__ __forceinline__ bool capsule_tight_hit(const Capsule& c, const float (&t)[8], V3 p) {
+  const float apx = p.x - c.ax, apy = p.y - c.ay, apz = p.z - c.az;
+  const float d = fmaf(apz, t[2], fmaf(apy, t[1], apx * t[0]));
+  const float nt = -__saturatef(d * t[3]);                                   // -clamp(t, 0, 1); NaN -> 0
+  const float ex = fmaf(nt, t[0], apx), ey = fmaf(nt, t[1], apy), ez = fmaf(nt, t[2], apz);
+  return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < t[4];
+}
 // The capsules alone, position only (the streaming kernel pushes out of the sphere in packed form first).
 template <class M>
 __device__ __forceinline__ V3 collide_caps_pos_bounded(const StepArgs& a, V3 p) {
 #pragma unroll 1
   for (int q = 0; q < a.ncaps; ++q) {
-    if (!capsule_bound_hit(a.capb[q], p)) continue;
+    if (!capsule_tight_hit(a.caps[q], a.capt[q], p)) continue;
     const float r = a.caps[q].r;
     p = collide_pos<M>(p, capsule_center<M>(a.caps[q], p), r, M::mul(r, r));
   }
@@ -91,7 +103,7 @@ __device__ __forceinline__ void collide_all_pos_vel_bounded(const StepArgs& a, V
   collide_pos_vel<M>(p, w, V3{ a.cx, a.cy, a.cz }, a.r, a.r2);
 #pragma unroll 1
   for (int q = 0; q < a.ncaps; ++q) {
-    if (!capsule_bound_hit(a.capb[q], p)) continue;
+    if (!capsule_tight_hit(a.caps[q], a.capt[q], p)) continue;
     const float r = a.caps[q].r;
     collide_pos_vel<M>(p, w, capsule_center<M>(a.caps[q], p), r, M::mul(r, r));
   }

@@ -40,6 +40,9 @@ struct StepArgs {
   // ... and a capsule-shaped second bound for the warps the first one lets through: axis (b - a), 1 / |b - a|^2 (0 for a
   // degenerate capsule) and the squared radius with its margin, for a packed fast-arithmetic distance to the axis.
   float capt[kMaxCapsules][8];   // abx, aby, abz, inv_l2, r2_tight, 0, 0, 0
+  // ... and in front of both, the shell around the sphere's centre that holds all capsules (squared radii, with margins):
+  // the step already has every vertex's squared distance to that centre.
+  float cap_lo2, cap_hi2;
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.

@@ -37,6 +37,7 @@
 #include <cuda.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -48,7 +49,10 @@ namespace {
 typedef unsigned long long u64;
 
 constexpr int kK = 8;                            // constraint iterations == pipeline depth == vertices per chunk
-constexpr int kWarps = 4;
+#ifndef BH_STREAM_WARPS
+#define BH_STREAM_WARPS 4
+#endif
+constexpr int kWarps = BH_STREAM_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kPlaneTile = 32 * 128;             // bytes of one plane of one chunk: 32 strands x 8 vertices x 16 B
 constexpr int kStageBytes = 2 * kPlaneTile;      // position + velocity
@@ -106,6 +110,11 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 constexpr u64 kOne2 = 0x3f8000003f800000ull;
 constexpr u64 kHalf2 = 0x3f0000003f000000ull;
 
+#ifdef BH_STATS   // debug build only (tools/stats_build.sh): contact statistics of the step loop, printed by the last warp of a launch
+__device__ unsigned long long g_stats[16];
+#define BH_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#endif
+
 struct V3p { u64 x, y, z; };                     // lo half: stage a, hi half: stage a + 4
 
 // Packed counterparts of MathExact / MathFast (hair_math.cuh). `nz` is (-0.0f, -0.0f) from a kernel parameter.
@@ -161,6 +170,15 @@ __device__ __forceinline__ V3p sub3(V3p a, V3p b) { return { sub2(a.x, b.x), sub
 __device__ __forceinline__ V3 lo3(V3p v) { return { lo(v.x), lo(v.y), lo(v.z) }; }
 __device__ __forceinline__ V3 hi3(V3p v) { return { hi(v.x), hi(v.y), hi(v.z) }; }
 __device__ __forceinline__ V3p pk3(V3 l, V3 h) { return { pk(l.x, h.x), pk(l.y, h.y), pk(l.z, h.z) }; }
+
+// (d < r) ? t : f per component, as one FSETP and three FSEL: left to itself ptxas writes such a select, when its result goes
+// to a register of its own, as two predicated moves per component
+__device__ __forceinline__ V3 sel3_lt(float d, float r, V3 t, V3 f) {
+  V3 o;
+  asm("{\n.reg .pred p;\nsetp.lt.f32 p, %9, %10;\nselp.f32 %0, %3, %6, p;\nselp.f32 %1, %4, %7, p;\nselp.f32 %2, %5, %8, p;\n}"
+      : "=f"(o.x), "=f"(o.y), "=f"(o.z) : "f"(t.x), "f"(t.y), "f"(t.z), "f"(f.x), "f"(f.y), "f"(f.z), "f"(d), "f"(r));
+  return o;
+}
 
 // vec3(mat4(1.0) * vec4(p, 1.0)) in GLM's operation order (see root_transform in hair_step.cu).
 template <class M>
@@ -393,21 +411,34 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
     dpc[q] = PM::dot(pt[q], pt[q], nz);
   }
-  if (RS == 8) {                                                            // roots do not collide (cs:149-151: index > 0)
+  // roots do not collide (cs:149-151: index > 0): their distance becomes +inf, which no radius exceeds; in the capsule variant
+  // NaN, which the minimum AND the maximum below skip (fminf / fmaxf return the other operand) and which compares false too
+  const float no_hit = __int_as_float(CAPS ? 0x7fffffff : 0x7f800000);
+  if (RS == 8) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (j == q) dpc[q] = pk(__int_as_float(0x7f800000), hi(dpc[q]));
-      if (j == q + 4) dpc[q] = pk(lo(dpc[q]), __int_as_float(0x7f800000));
+      if (j == q) dpc[q] = pk(no_hit, hi(dpc[q]));
+      if (j == q + 4) dpc[q] = pk(lo(dpc[q]), no_hit);
     }
   } else if (RS == 4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (root_in_stage<RS>(j, q)) dpc[q] = pk(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+      if (root_in_stage<RS>(j, q)) dpc[q] = pk(no_hit, no_hit);
   }
   const float mnc = min8(dpc);
 
   // ---- phase B: push-outs, only when some lane of the warp touches the sphere --------------------
   const bool any_hit = __any_sync(0xffffffffu, mnc < a.r2);
+#ifdef BH_STATS
+  {
+    int pairs = 0, stages = 0, lanes = 0;
+    for (int q = 0; q < 4; ++q) {
+      const unsigned ml = __ballot_sync(0xffffffffu, lo(dpc[q]) < a.r2), mh = __ballot_sync(0xffffffffu, hi(dpc[q]) < a.r2);
+      pairs += (ml | mh) != 0; stages += (ml != 0) + (mh != 0); lanes += __popc(ml) + __popc(mh);
+    }
+    if ((threadIdx.x & 31) == 0) { BH_STAT(0, 1); BH_STAT(1, any_hit); BH_STAT(2, pairs); BH_STAT(3, stages); BH_STAT(4, lanes); BH_STAT(5, SEP); }
+  }
+#endif
   V3p C[4];
   auto sphere_push_out = [&]() {
     // a hit has dpc < r2 < inf (launcher guarantees), so only the lower bound of the branch-free range can fail
@@ -417,10 +448,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const V3p Q = PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
-      const bool hl = lo(dpc[q]) < a.r2, hh = hi(dpc[q]) < a.r2;
-      C[q].x = pk(hl ? lo(Q.x) : lo(D[q].x), hh ? hi(Q.x) : hi(D[q].x));
-      C[q].y = pk(hl ? lo(Q.y) : lo(D[q].y), hh ? hi(Q.y) : hi(D[q].y));
-      C[q].z = pk(hl ? lo(Q.z) : lo(D[q].z), hh ? hi(Q.z) : hi(D[q].z));
+      C[q] = pk3(sel3_lt(lo(dpc[q]), a.r2, lo3(Q), lo3(D[q])), sel3_lt(hi(dpc[q]), a.r2, hi3(Q), hi3(D[q])));
     }
     // stage 7 is done: keep its final position and the collision normal for the step that writes it out
     s.heldHit = hi(dpc[3]) < a.r2;
@@ -436,12 +464,37 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     if (any_hit) { sphere_push_out(); enter_through_P(); }
     return any_hit;
   }
-  // ---- capsule extension: bound test on the positions as the sphere left them, exact chain out of line ------------
+  // ---- capsule extension: bound tests on the positions as the sphere left them, exact chain out of line ------------
+  // Level 0, nearly free: the squared distances to the sphere centre are there already. All capsules lie inside the shell
+  // cap_lo2 < |p - c|^2 < cap_hi2 (fill_capsule_bounds, with margins). The push-out above only moves a vertex outwards, onto
+  // the sphere, and cap_lo2 is either beyond the sphere's surface or zero: a warp whose eight positions all stayed below
+  // cap_lo2 or above cap_hi2 BEFORE the push-out has none inside the shell after it.
+  bool any_cap = __any_sync(0xffffffffu, mnc < a.cap_hi2 && max8(dpc) > a.cap_lo2);
+#ifdef BH_STATS
+  if ((threadIdx.x & 31) == 0) BH_STAT(6, any_cap);
+#endif
+  // level 1: a bounding sphere per capsule. Written out for both kinds of step so that the common one — the sphere touched
+  // nobody, and no bounding sphere either — reads the positions where they are (D) and leaves without having copied them.
+  if (!any_hit) {
+    s.heldHit = false;
+    if (any_cap) any_cap = __any_sync(0xffffffffu, caps_may_touch(a, D));
+#ifdef BH_STATS
+    if ((threadIdx.x & 31) == 0) BH_STAT(7, any_cap);
+#endif
+    if (!any_cap) { s.heldCap = false; return false; }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) C[q] = D[q];
-  if (any_hit) sphere_push_out(); else s.heldHit = false;
-  bool any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
-  if (any_cap) any_cap = __any_sync(0xffffffffu, caps_tight_touch(a, C));     // rare: only behind the bounding spheres
+    for (int q = 0; q < 4; ++q) C[q] = D[q];
+  } else {
+    sphere_push_out();                                                        // sets every C[q]
+    if (any_cap) any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
+#ifdef BH_STATS
+    if ((threadIdx.x & 31) == 0) BH_STAT(7, any_cap);
+#endif
+  }
+  if (any_cap) any_cap = __any_sync(0xffffffffu, caps_tight_touch(a, C));     // level 2: distance to the axis, fast arithmetic
+#ifdef BH_STATS
+  if ((threadIdx.x & 31) == 0) BH_STAT(8, any_cap);
+#endif
   if (any_cap) {
     // every vertex in flight that is not a root (cs:149-151: index > 0); the vertex in stage 7 is skipped, the next step
     // recomputes its whole chain (sphere included) together with its velocity
@@ -544,7 +597,14 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   auto leave = [&]() {
     if (lane == 0) {
       __threadfence();
-      if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) { tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence(); }
+      if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) {
+        tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence();
+#ifdef BH_STATS
+        printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: shell %llu spheres %llu tight %llu\n", g_stats[0], g_stats[1], g_stats[2],
+               g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[7], g_stats[8]);
+        for (int i = 0; i < 16; ++i) g_stats[i] = 0;
+#endif
+      }
     }
   };
   int tC = grab(), cC = 0;
@@ -666,6 +726,35 @@ struct DeviceInfo { int sms = 0; bool ready[24] = {}; int blocks_per_sm[24] = {}
 // widened by 1e-3 relative + 1e-6 absolute — orders of magnitude above the fp32 rounding of either the bound or the exact
 // test it guards, so "outside the bound" implies "the exact test cannot fire".
 void fill_capsule_bounds(StepArgs& b) {
+  // Level 0: the shell around the sphere's centre that contains every capsule, lo <= |p - c| <= hi for each of their points:
+  // lo = min_k (distance from c to axis k - r_k), hi = max_k (farthest axis end + r_k); margins as below. lo only counts when
+  // it lies beyond the sphere's surface (a vertex pushed out of the sphere lands ON it), otherwise it is zero.
+  {
+    double lo = INFINITY, hi = 0.0;
+    bool bad = false;
+    for (int k = 0; k < b.ncaps && k < kMaxCapsules; ++k) {
+      const Capsule& c = b.caps[k];
+      const double ax = (double)c.ax - b.cx, ay = (double)c.ay - b.cy, az = (double)c.az - b.cz;
+      const double ux = (double)c.bx - c.ax, uy = (double)c.by - c.ay, uz = (double)c.bz - c.az;
+      const double l2 = ux * ux + uy * uy + uz * uz;
+      double t = l2 > 0.0 ? -(ax * ux + ay * uy + az * uz) / l2 : 0.0;
+      t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+      const double nx = ax + t * ux, ny = ay + t * uy, nz = az + t * uz;
+      const double dnear = std::sqrt(nx * nx + ny * ny + nz * nz), r = std::fabs((double)c.r);
+      const double da = std::sqrt(ax * ax + ay * ay + az * az);
+      const double bx = ax + ux, by = ay + uy, bz = az + uz, db = std::sqrt(bx * bx + by * by + bz * bz);
+      if (!std::isfinite(dnear) || !std::isfinite(da) || !std::isfinite(db) || !std::isfinite(r)) bad = true;
+      lo = std::fmin(lo, dnear - r);
+      hi = std::fmax(hi, std::fmax(da, db) + r);
+    }
+    lo = lo * (1.0 - 1e-3) - 1e-6;
+    hi = hi * (1.0 + 1e-3) + 1e-6;
+    const double rs = std::fabs((double)b.r) * (1.0 + 2e-3) + 1e-6;          // where a pushed-out vertex can end up, generously
+    float lo2 = (!bad && lo > rs) ? std::nextafter((float)(lo * lo), 0.0f) : 0.0f;
+    float hi2 = !bad ? std::nextafter((float)(hi * hi), INFINITY) : INFINITY;
+    if (!(lo2 == lo2) || !(hi2 == hi2) || !std::isfinite((double)b.cx + b.cy + b.cz) || !std::isfinite(b.r)) { lo2 = 0.0f; hi2 = INFINITY; }
+    b.cap_lo2 = lo2; b.cap_hi2 = hi2;
+  }
   for (int k = 0; k < b.ncaps && k < kMaxCapsules; ++k) {
     const Capsule& c = b.caps[k];
     const double hx = 0.5 * ((double)c.bx - c.ax), hy = 0.5 * ((double)c.by - c.ay), hz = 0.5 * ((double)c.bz - c.az);

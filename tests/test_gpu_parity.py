@@ -520,6 +520,11 @@ CAPSULE_SETS = {
     # overflows, a capsule far from the origin, a zero radius, a NaN end point
     "extreme": [((-1.0e20, 0.3, 0.0), (1.0e20, 0.3, 0.0), 0.4), ((1.0e6, 0.0, 0.0), (1.0e6, 1.0, 0.0), 0.5),
                 ((0.2, 0.9, 0.1), (0.4, 1.2, 0.1), 0.0), ((float("nan"), 0.0, 0.0), (0.0, 1.0, 0.0), 0.3)],
+    # the shell test in front of the per-capsule bounds (squared distance to the sphere's centre, already known, against the
+    # range of distances at which capsules exist): one capsule well beyond the sphere where the strands hang (lower bound
+    # active), one entirely inside the sphere (never reached once the sphere has pushed a vertex out), one across its surface
+    "shell": [((-0.5, -1.45, 0.0), (0.5, -1.45, 0.1), 0.15), ((0.1, 0.2, 0.0), (0.3, 0.3, 0.1), 0.25),
+              ((0.0, 0.9, 0.0), (0.05, 1.3, 0.0), 0.2)],
     # eight capsules (the maximum) in a ring below the scalp, where the strands hang
     "ring8": [((float(np.cos(k * np.pi / 4)), -1.1, float(np.sin(k * np.pi / 4))),
                (float(np.cos((k + 1) * np.pi / 4)), -1.25, float(np.sin((k + 1) * np.pi / 4))), 0.12) for k in range(8)],
@@ -560,6 +565,28 @@ def test_stream_kernel_capsules_bit_exact(caps, S, N, sphere):
             d = np.linalg.norm(x - (a + t[:, None] * ab), axis=1)
             on |= np.abs(d - r) < 1e-5
         assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
+
+
+@pytest.mark.parametrize("sphere", [(0.0, 0.0, 0.0, 5.0), (0.0, 0.0, 0.0, 0.0), (0.3, 2.0, 0.1, 1.2), (0.0, 0.0, 0.0, 1.0e-3), (1.0e3, 0.0, 0.0, 1.0)])
+@pytest.mark.parametrize("caps", ["arms", "shell", "overlap"])
+def test_stream_kernel_capsules_any_sphere_bit_exact(caps, sphere):
+    """The capsule bounds measure distances from the SPHERE's centre: spheres that swallow every capsule and every strand
+    (all vertices end on its surface), of radius zero, off to the side, tiny, or a thousand units away stay bit-exact."""
+    S, N = 1300, 16
+    pos, vel = ragged_state(S, N)
+    par, gcfg = _capsule_params(CAPSULE_SETS[caps], dt=float(DT), scale=1.45, sphere=sphere)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(8):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        assert sim.kernel_kind == 0
+        sim.upload(pos, vel)
+        for _ in range(8):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
 
 
 def test_stream_kernel_capsules_fast_profile_close_to_exact():
