@@ -95,6 +95,42 @@ int unmap_gl(bh_sim* s) {
 using bh::map_gl;
 using bh::unmap_gl;
 
+namespace {
+// The sim's work moves to another stream: everything already queued on the old one comes first. All steps of a sim share one
+// tile-scheduler slot and update the state in place, so two steps may never overlap — without this, back-to-back steps
+// issued on two different streams could.
+int switch_stream(bh_sim* s, cudaStream_t next) {
+  if (next == s->stream) return BH_OK;
+  DeviceGuard g(s->device);
+  if (!s->order_event) BH_CUDA(cudaEventCreateWithFlags(&s->order_event, cudaEventDisableTiming));
+  BH_CUDA(cudaEventRecord(s->order_event, s->stream));
+  BH_CUDA(cudaStreamWaitEvent(next, s->order_event, 0));
+  s->stream = next;
+  return BH_OK;
+}
+
+// launch_step, and after a failure the scheduler words back to their idle state (a launch that died half-way leaves its
+// tile counter wherever it was, and every later launch on this slot would skip those tiles).
+cudaError_t launch_step_checked(bh_sim* s, const bh::StepArgs& a, cudaStream_t stream, unsigned int* words) {
+  const cudaError_t e = bh::launch_step(a, s->params.math, stream, words);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); (void)cudaMemsetAsync(words, 0, 2 * sizeof(unsigned int), stream); (void)cudaGetLastError(); }
+  return e;
+}
+
+// Maps the registered GL buffer for the lifetime of the object: every way out of an entry point, the early returns of
+// BH_CUDA included, leaves the buffer unmapped (the renderer cannot touch a mapped buffer). done() unmaps explicitly and
+// reports the unmap's own status on the regular path.
+struct GlMapped {
+  bh_sim* s; int rc; bool mapped;
+  explicit GlMapped(bh_sim* sim) : s(sim), rc(map_gl(sim)), mapped(rc == BH_OK) {
+    if (!mapped && s->gl_resource) (void)cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream), (void)cudaGetLastError();   // a map that failed half-way
+  }
+  int done() { if (!mapped) return rc; mapped = false; return unmap_gl(s); }
+  ~GlMapped() { if (mapped) { (void)unmap_gl(s); } }
+  GlMapped(const GlMapped&) = delete; GlMapped& operator=(const GlMapped&) = delete;
+};
+}  // namespace
+
 extern "C" {
 
 const char* bh_last_error(void) { return g_last_error.c_str(); }
@@ -154,20 +190,19 @@ int bh_destroy(bh_sim* s) {
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : s->host_events) cudaEventDestroy(ev);
+  if (s->order_event) cudaEventDestroy(s->order_event);
   delete s;
   return BH_OK;
 }
 
 int bh_set_stream(bh_sim* s, void* cuda_stream) {
   if (!s) return fail(BH_ERR_INVALID, "bh_set_stream: sim is NULL");
-  s->stream = static_cast<cudaStream_t>(cuda_stream);
-  return BH_OK;
+  return switch_stream(s, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int bh_reset_stream(bh_sim* s) {
   if (!s) return fail(BH_ERR_INVALID, "bh_reset_stream: sim is NULL");
-  s->stream = s->own_stream;
-  return BH_OK;
+  return switch_stream(s, s->own_stream);
 }
 
 int bh_synchronize(bh_sim* s) {
@@ -203,10 +238,10 @@ int bh_upload(bh_sim* s, const float* pos4, const float* vel4, const float* tan4
   DeviceGuard g(s->device);
   const size_t bytes = (size_t)s->nvertices * sizeof(float4);
   const float* src[BH_NUM_PLANES] = { pos4, vel4, tan4 };
-  int rc = map_gl(s); if (rc) return rc;
+  GlMapped gl(s); if (gl.rc) return gl.rc;
   for (int p = 0; p < BH_NUM_PLANES; ++p)
     if (src[p]) BH_CUDA(cudaMemcpyAsync(s->planes[p], src[p], bytes, cudaMemcpyHostToDevice, s->stream));
-  rc = unmap_gl(s); if (rc) return rc;
+  if (int rc = gl.done()) return rc;
   BH_CUDA(cudaStreamSynchronize(s->stream));
   if (pos4) s->initialized = true;
   return BH_OK;
@@ -217,10 +252,10 @@ int bh_download(bh_sim* s, float* pos4, float* vel4, float* tan4) {
   DeviceGuard g(s->device);
   const size_t bytes = (size_t)s->nvertices * sizeof(float4);
   float* dst[BH_NUM_PLANES] = { pos4, vel4, tan4 };
-  int rc = map_gl(s); if (rc) return rc;
+  GlMapped gl(s); if (gl.rc) return gl.rc;
   for (int p = 0; p < BH_NUM_PLANES; ++p)
     if (dst[p]) BH_CUDA(cudaMemcpyAsync(dst[p], s->planes[p], bytes, cudaMemcpyDeviceToHost, s->stream));
-  rc = unmap_gl(s); if (rc) return rc;
+  if (int rc = gl.done()) return rc;
   BH_CUDA(cudaStreamSynchronize(s->stream));
   return BH_OK;
 }
@@ -336,7 +371,7 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_step: no strand state (call bh_upload / bh_init_* first)");
   if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step: substeps < 1");
   DeviceGuard g(s->device);
-  int rc = map_gl(s); if (rc) return rc;
+  GlMapped gl(s); if (gl.rc) return gl.rc;
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
   static const bool zigzag = [] { const char* e = getenv("BH_NO_ZIGZAG"); return !(e && e[0] == '1'); }();
@@ -345,20 +380,20 @@ int bh_step(bh_sim* s, float dt, int substeps) {
     // order per strand, so the result is bit-identical to `substeps` launches; HBM sees the state once per frame.
     a.passes = substeps;
     a.reverse = zigzag ? (int)(s->step_launches & 1) : 0;
-    BH_CUDA(bh::launch_step(a, s->params.math, s->stream, s->tile_counters + 32 * kHostPipeStreams));
+    BH_CUDA(launch_step_checked(s, a, s->stream, s->tile_counters + 32 * kHostPipeStreams));
     s->launches += 1;
     s->step_launches += 1;
-    return unmap_gl(s);
+    return gl.done();
   }
   for (int q = 0; q < substeps; ++q) {
     // Consecutive launches walk the shard in opposite directions: a launch starts with the tiles the previous one wrote
     // last, which are still in the 126 MB L2 — those reads, and the write-backs they replace, never reach HBM.
     a.reverse = zigzag ? (int)(s->step_launches & 1) : 0;
-    BH_CUDA(bh::launch_step(a, s->params.math, s->stream, s->tile_counters + 32 * kHostPipeStreams));
+    BH_CUDA(launch_step_checked(s, a, s->stream, s->tile_counters + 32 * kHostPipeStreams));
     s->launches += 1;
     s->step_launches += 1;
   }
-  return unmap_gl(s);
+  return gl.done();
 }
 
 int bh_set_substep_fusion(bh_sim* s, int enabled) {
@@ -414,9 +449,9 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
     bh::StepArgs a = make_args(s, h, dP, dV, count);
     if (e == cudaSuccess && s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
       a.passes = substeps;                                                  // the substeps of the slice as passes of one launch
-      e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1;
+      e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1;
     } else {
-      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1; }
     }
     if (e == cudaSuccess) e = cudaEventRecord(stepped, run);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(down, stepped, 0);
@@ -462,9 +497,9 @@ int bh_step_readback(bh_sim* s, float dt, int substeps, float* pos4) {
     bh::StepArgs a = make_args(s, h, dP, s->planes[BH_PLANE_VELOCITY] + off, count);
     if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
       a.passes = substeps;
-      e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1;
+      e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1;
     } else {
-      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = bh::launch_step(a, s->params.math, run, s->tile_counters); s->launches += 1; }
+      for (int q = 0; q < substeps && e == cudaSuccess; ++q) { e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1; }
     }
     cudaEvent_t stepped = s->host_events[2 * k];
     if (e == cudaSuccess) e = cudaEventRecord(stepped, run);
@@ -537,11 +572,11 @@ int bh_skin_roots(bh_sim* s, const float* dq_palette, int njoints) {
     s->skin_dq_cap = njoints;
   }
   BH_CUDA(cudaMemcpyAsync(s->skin_dq, dq_palette, sizeof(float) * 8 * (size_t)njoints, cudaMemcpyHostToDevice, s->stream));
-  int rc = map_gl(s); if (rc) return rc;
+  GlMapped gl(s); if (gl.rc) return gl.rc;
   BH_CUDA(bh::launch_skin_roots_dq(s->skin_rest3, s->skin_joints4, s->skin_weights3, s->skin_dq, s->nstrands, s->nverts,
                                    s->planes[BH_PLANE_POSITION], s->stream));
   s->launches += 1;
-  rc = unmap_gl(s); if (rc) return rc;
+  if (int rc = gl.done()) return rc;
   // the palette is pageable host memory owned by the caller: do not return before it was consumed
   BH_CUDA(cudaStreamSynchronize(s->stream));
   return BH_OK;
@@ -577,12 +612,12 @@ int bh_tess_stream(bh_sim* s, const bh_tess_params* t, float* out4_host) {
     BH_CUDA(cudaMalloc(&s->tess_out, sizeof(float4) * (size_t)count));
     s->tess_out_cap = count;
   }
-  int rc = map_gl(s); if (rc) return rc;
+  GlMapped gl(s); if (gl.rc) return gl.rc;
   BH_CUDA(bh::launch_tess_stream(s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_TANGENT], s->tess_patch, s->tess_npatches, s->nverts,
                                  s->params.scale, t->ninstances, t->nlines, t->nsubsegments, t->seed, s->tess_out, s->stream));
   s->launches += 1;
   s->tess_out_count = count;
-  rc = unmap_gl(s); if (rc) return rc;
+  if (int rc = gl.done()) return rc;
   if (out4_host) {
     BH_CUDA(cudaMemcpyAsync(out4_host, s->tess_out, sizeof(float4) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     BH_CUDA(cudaStreamSynchronize(s->stream));
@@ -610,8 +645,13 @@ int bh_register_gl_buffer(bh_sim* s, unsigned int gl_buffer) {
   if (rc) { cudaGraphicsUnregisterResource(res); s->gl_resource = nullptr; for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p]; return rc; }
   cudaError_t e = cudaMemcpyAsync(s->planes[0], s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
   rc = unmap_gl(s);
-  if (e != cudaSuccess) return fail(BH_ERR_CUDA, "bh_register_gl_buffer: copy into GL buffer", e);
-  return rc;
+  if (e != cudaSuccess || rc) {                                             // the state never reached the GL buffer: keep stepping our own
+    (void)cudaGetLastError();
+    cudaGraphicsUnregisterResource(res); s->gl_resource = nullptr;
+    for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p];
+    return e != cudaSuccess ? fail(BH_ERR_CUDA, "bh_register_gl_buffer: copy into GL buffer", e) : rc;
+  }
+  return BH_OK;
 }
 
 int bh_unregister_gl_buffer(bh_sim* s) {

@@ -48,6 +48,7 @@ struct bh_sim {
   bool fuse_substeps = false;            // bh_set_substep_fusion: the substeps of a bh_step as passes of one launch
   int64_t launches = 0;
   int64_t step_launches = 0;             // launches of bh_step alone: parity = tile direction of the next one
+  cudaEvent_t order_event = nullptr;     // bh_set_stream / bh_reset_stream: the new stream waits for what the old one holds
   std::vector<cudaEvent_t> host_events;  // bh_step_host: two per slice + one, created on first use
   unsigned int* tile_counters = nullptr;  // kHostPipeStreams + 1 words: one tile scheduler per stream that may be in flight
   // roots kept for re-generation / skinning ("base normals are kept for potential future uses", hair.cc:262)

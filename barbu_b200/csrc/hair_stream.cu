@@ -795,6 +795,7 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS, CAPS, FUSED>;
+  int sms = 0, blocks_per_sm = 0;                                           // copies taken under the lock
   {
     std::lock_guard<std::mutex> g(mu);
     DeviceInfo& di = info[dev];
@@ -805,9 +806,12 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
       if (di.blocks_per_sm[variant] < 1) return cudaErrorLaunchOutOfResources;
       di.ready[variant] = true;
     }
+    sms = di.sms; blocks_per_sm = di.blocks_per_sm[variant];
   }
   // Tensor maps are pure functions of (plane address, shape): keep the last few so a frame of substeps on the same
-  // shard (or the slices of bh_step_host) does not re-encode them at every launch.
+  // shard (or the slices of bh_step_host) does not re-encode them at every launch. Process-wide and never invalidated on
+  // purpose: an entry whose buffer was freed can only be hit again by a new buffer at the same address with the same shape,
+  // for which the encoded map is the same 128 bytes (cuTensorMapEncodeTiled reads its arguments, not the memory).
   struct MapEntry { const void* pos; const void* vel; long long s; int n; CUtensorMap mapP, mapV; };
   static MapEntry cache[64];
   static int cache_next = 0;
@@ -835,9 +839,9 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   const long long ngroups = ntiles / a.group_tiles;
   long long blocks = (ngroups + kWarps - 1) / kWarps;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
-  int per_sm = info[dev].blocks_per_sm[variant];
+  int per_sm = blocks_per_sm;
   if (occ_cap > 0 && occ_cap < per_sm) per_sm = occ_cap;
-  const long long resident = (long long)info[dev].sms * per_sm;
+  const long long resident = (long long)sms * per_sm;
   if (blocks > resident) blocks = resident;
   kernel<<<(unsigned)blocks, kThreads, kSmemBytes, stream>>>(a, mapP, mapV, tile_counter);
   return cudaGetLastError();

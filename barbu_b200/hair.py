@@ -629,6 +629,7 @@ class Hair:
 
     def setup(self, scalp):
         """`scalp`: a ScalpMesh, or the path of an OBJ scalp resource as in Application.cc:38-39."""
+        self.deinit()                                                       # a second setup starts over, like barbu_hair.hpp
         if isinstance(scalp, (str, os.PathLike)):
             try:
                 scalp = load_obj_scalp(os.fspath(scalp))

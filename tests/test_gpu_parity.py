@@ -411,8 +411,37 @@ def test_hair_module_mirror():
     assert_bit_equal(gt2, gt, "tangent plane untouched by the simulation")
     # the tess-stream half of render(), default tessellation (hair.h:33-35)
     assert_bit_equal(hair.stream(), po.tess_stream(pos, gt, hair.patch_indices, N, 1.45, 3, 2, 16, 1234), "tess-stream")
+    # a second setup starts over: new sim, patches uploaded again, same results as a fresh module
+    hair.setup(bb.ScalpMesh(root_pos, root_nrm, tri))
+    assert hair.initialized() and hair.nroots == 448
+    gp2, _, gt3 = hair.sim.download(tan=True)
+    pos0 = sphere_state(rows, cols, N)[4]
+    assert_bit_equal(gp2, pos0, "state after a second setup")
+    assert_bit_equal(hair.stream(), po.tess_stream(pos0, gt3, hair.patch_indices, N, 1.45, 3, 2, 16, 1234), "tess-stream after a second setup")
     hair.deinit()
     assert not hair.initialized() and hair.stream() is None
+
+
+def test_switching_streams_keeps_steps_in_order():
+    """bh_set_stream / bh_reset_stream order the new stream after the work queued on the old one: steps issued back to back
+    on alternating streams (they share one tile scheduler and update the state in place) equal the same steps on one stream."""
+    import torch
+    S, N = 1 << 16, 32
+    pos, vel = ragged_state(S, N)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    with bb.HairSim(S, N) as a, bb.HairSim(S, N) as b:
+        for sim in (a, b):
+            sim.configure(scale=1.45, sphere=SPHERE)
+            sim.upload(pos, vel)
+        for k in range(12):
+            a.step(float(DT), 2)
+        for k in range(12):
+            if k % 4 == 3: b.reset_stream()
+            else: b.set_stream(streams[k % 3].cuda_stream)
+            b.step(float(DT), 2)                                             # no host synchronisation in between
+        wp, wv, _ = a.download()
+        gp, gv, _ = b.download()
+    assert_bit_equal(gp, wp, "positions"); assert_bit_equal(gv, wv, "velocities")
 
 
 # ---- streaming kernel (TMA tiles, persistent warps, packed fp32x2) ---------------------------------
