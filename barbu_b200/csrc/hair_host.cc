@@ -148,8 +148,8 @@ int bh_sphere_scalp_triangles_ordered(int rows, int cols, int order, int32_t* tr
 // corner splits the quad into (x, y, z), (z, ext, x) (l.201-208); indices are 1-based in the file.
 // MeshData::setup (src/memory/resources/mesh_data.cc:384-406): vertices are re-indexed in first-appearance order of the
 // unique (v, vt, vn) triples over the corner list; vertex j takes position[v] and normal[vn]. One root per vertex
-// (src/fx/hair.cc:58). A scalp without normals would get per-corner normals from recalculateNormals
-// (src/utils/raw_mesh_file.cc:11-50) and 3 strands per face; that path is not restated: BH_ERR_UNSUPPORTED.
+// (src/fx/hair.cc:58). A scalp without normals gets per-corner normals as recalculateNormals makes them
+// (src/utils/raw_mesh_file.cc:11-50) and so 3 strands per face.
 int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nvertices, int32_t** tri, int64_t* nfaces) {
   if (!path || !pos3 || !nrm3 || !nvertices || !tri || !nfaces) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: NULL argument");
   *pos3 = *nrm3 = nullptr; *tri = nullptr; *nvertices = *nfaces = 0;
@@ -187,7 +187,26 @@ int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nve
     }
   }
   if (corners.empty() || positions.empty()) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: no faces or no positions in the file");
-  if (normals.empty()) return BH_ERR_UNSUPPORTED;
+  if (normals.empty()) {
+    // A scalp without `vn` lines: MeshData::setup recalculates (mesh_data.cc:366-372 -> RawMeshData::recalculateNormals,
+    // src/utils/raw_mesh_file.cc:11-50). Per face the unit normal of (v2 - v1) x (v3 - v2) is added, unweighted, to its three
+    // vertices; the sums are normalised; then every CORNER receives a normal entry of its own (a copy of its vertex's), so
+    // the re-indexing below sees 3 * F unique triples — one root per face corner. GLM arithmetic: cross as written in
+    // func_geometric.inl:74-77, dot = (x*x + y*y) + z*z, normalize = v * (1 / sqrt(dot)).
+    for (const I3& c : corners)
+      if (c.v < 1 || (size_t)c.v > positions.size()) return bh_host_fail(BH_ERR_INVALID, "bh_load_obj_scalp: face index outside the v list");
+    std::vector<V3> sum(positions.size(), V3{ 0.f, 0.f, 0.f });
+    auto unit = [](V3 a) { const float inv = 1.0f / std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); return V3{ a.x * inv, a.y * inv, a.z * inv }; };
+    for (size_t f3 = 0; f3 + 2 < corners.size(); f3 += 3) {
+      const V3 &p1 = positions[corners[f3].v - 1], &p2 = positions[corners[f3 + 1].v - 1], &p3 = positions[corners[f3 + 2].v - 1];
+      const V3 u{ p2.x - p1.x, p2.y - p1.y, p2.z - p1.z }, w{ p3.x - p2.x, p3.y - p2.y, p3.z - p2.z };
+      const V3 n = unit(V3{ u.y * w.z - w.y * u.z, u.z * w.x - w.z * u.x, u.x * w.y - w.x * u.y });
+      for (int k = 0; k < 3; ++k) { V3& a = sum[corners[f3 + k].v - 1]; a.x += n.x; a.y += n.y; a.z += n.z; }
+    }
+    for (V3& a : sum) a = unit(a);
+    normals.reserve(corners.size());
+    for (I3& c : corners) { normals.push_back(sum[c.v - 1]); c.n = (int)normals.size(); }   // 1-based like the file's own indices
+  }
   std::map<std::tuple<int, int, int>, int32_t> seen;
   std::vector<I3> unique;
   std::vector<int32_t> indices;
@@ -212,6 +231,48 @@ int bh_load_obj_scalp(const char* path, float** pos3, float** nrm3, int64_t* nve
   }
   std::memcpy(T, indices.data(), sizeof(int32_t) * 3 * nf);
   *pos3 = P; *nrm3 = Nn; *tri = T; *nvertices = (int64_t)nv; *nfaces = (int64_t)nf;
+  return BH_OK;
+}
+
+// ---- skinning palette from joint matrices --------------------------------------------------------------------------------
+// What SkeletonController::generate_skinning_datas (src/fx/animation/skeleton_controller.cc:248-265) hands the skinning
+// shader per joint, from the two matrices it has: S = global_pose * inverse_bind; the 3 x 4 skinning matrix is the top three
+// ROWS of S (l.255: first three columns of the transpose); glm::dualquat(mat3x4) (gtx/dual_quaternion.inl:303-351) takes the
+// rotation by the usual largest-diagonal case split and the dual part as 0.5 * translation * rotation. Matrices arrive in
+// GLM's layout (16 floats, column-major: element (row r, column c) at [4 * c + r]).
+int bh_dq_palette_from_matrices(const float* global_pose16, const float* inverse_bind16, int njoints, float* dq_palette) {
+  if (!global_pose16 || !inverse_bind16 || !dq_palette || njoints < 0) return bh_host_fail(BH_ERR_INVALID, "bh_dq_palette_from_matrices: bad argument");
+  for (int j = 0; j < njoints; ++j) {
+    const float* G = global_pose16 + 16 * (size_t)j;
+    const float* I = inverse_bind16 + 16 * (size_t)j;
+    float row[3][4];                                                         // row[r][c] = S(r, c), r < 3; the product in GLM's order of operations
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c)
+        row[r][c] = ((G[r] * I[4 * c] + G[4 + r] * I[4 * c + 1]) + G[8 + r] * I[4 * c + 2]) + G[12 + r] * I[4 * c + 3];
+    const float m00 = row[0][0], m11 = row[1][1], m22 = row[2][2];
+    float qx, qy, qz, qw;
+    const float trace = m00 + m11 + m22;
+    if (trace > 0.0f) {
+      const float r = std::sqrt(1.0f + trace), k = 0.5f / r;
+      qw = 0.5f * r; qx = (row[2][1] - row[1][2]) * k; qy = (row[0][2] - row[2][0]) * k; qz = (row[1][0] - row[0][1]) * k;
+    } else if (m00 > m11 && m00 > m22) {
+      const float r = std::sqrt(1.0f + m00 - m11 - m22), k = 0.5f / r;
+      qx = 0.5f * r; qy = (row[1][0] + row[0][1]) * k; qz = (row[0][2] + row[2][0]) * k; qw = (row[2][1] - row[1][2]) * k;
+    } else if (m11 > m22) {
+      const float r = std::sqrt(1.0f + m11 - m00 - m22), k = 0.5f / r;
+      qx = (row[1][0] + row[0][1]) * k; qy = 0.5f * r; qz = (row[2][1] + row[1][2]) * k; qw = (row[0][2] - row[2][0]) * k;
+    } else {
+      const float r = std::sqrt(1.0f + m22 - m00 - m11), k = 0.5f / r;
+      qx = (row[0][2] + row[2][0]) * k; qy = (row[2][1] + row[1][2]) * k; qz = 0.5f * r; qw = (row[1][0] - row[0][1]) * k;
+    }
+    const float tx = row[0][3], ty = row[1][3], tz = row[2][3];
+    float* o = dq_palette + 8 * (size_t)j;
+    o[0] = qx; o[1] = qy; o[2] = qz; o[3] = qw;
+    o[4] = 0.5f * (tx * qw + ty * qz - tz * qy);
+    o[5] = 0.5f * (-tx * qz + ty * qw + tz * qx);
+    o[6] = 0.5f * (tx * qy - ty * qx + tz * qw);
+    o[7] = -0.5f * (tx * qx + ty * qy + tz * qz);
+  }
   return BH_OK;
 }
 

@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
     "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
-    "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_register_gl_buffer",
+    "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_dq_palette_from_matrices", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
     "bh_marschner_default_params", "bh_marschner_generate",
@@ -118,6 +118,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_step_host": ([vp, f32, C.c_int, vp, vp], C.c_int),
         "bh_set_substep_fusion": ([vp, C.c_int], C.c_int),
         "bh_step_readback": ([vp, f32, C.c_int, vp], C.c_int),
+        "bh_dq_palette_from_matrices": ([vp, vp, C.c_int, vp], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
@@ -557,6 +558,12 @@ class ScalpMesh:
     positions: np.ndarray                      # (S, 3) vertices[j].position
     normals: np.ndarray                        # (S, 3) vertices[j].normal
     indices: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))  # triangle list
+    # skinned scalps (glTF): JOINTS_0 / WEIGHTS_0 per vertex (mesh_data.h:69-72), and the skin that drives them
+    joints: Optional[np.ndarray] = None        # (S, 4) int32
+    weights: Optional[np.ndarray] = None       # (S, 4) float32
+    joint_nodes: Optional[list] = None
+    inverse_bind: Optional[np.ndarray] = None  # (J, 16) column-major
+    joint_rest_global: Optional[np.ndarray] = None   # (J, 16): the joints' world matrices in the file's rest pose
 
     @property
     def nvertices(self) -> int:
@@ -565,6 +572,132 @@ class ScalpMesh:
     @property
     def nfaces(self) -> int:
         return int(np.asarray(self.indices).reshape(-1, 3).shape[0])
+
+
+def dq_palette_from_matrices(global_pose, inverse_bind) -> np.ndarray:
+    """(J, 8) dual-quaternion palette for HairSim.skin_roots from the joints' global pose and inverse bind matrices, (J, 16)
+    each in GLM's column-major layout — SkeletonController::generate_skinning_datas (bh_dq_palette_from_matrices)."""
+    A = np.ascontiguousarray(global_pose, np.float32).reshape(-1, 16)
+    B = np.ascontiguousarray(inverse_bind, np.float32).reshape(-1, 16)
+    if A.shape != B.shape:
+        raise ValueError("one global pose and one inverse bind matrix per joint")
+    out = np.empty((A.shape[0], 8), np.float32)
+    _check(load_library().bh_dq_palette_from_matrices(_ptr(A), _ptr(B), A.shape[0], _ptr(out)))
+    return out
+
+
+_GLTF_COMPONENT = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+_GLTF_WIDTH = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
+
+
+def _glm_mat4_mul(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """A * B for 16-float column-major matrices, in GLM's order of operations (type_mat4x4.inl:643-646), binary32."""
+    A, B = A.astype(np.float32).reshape(4, 4), B.astype(np.float32).reshape(4, 4)        # [column][row]
+    R = np.empty((4, 4), np.float32)
+    for c in range(4):
+        R[c] = ((A[0] * B[c, 0] + A[1] * B[c, 1]) + A[2] * B[c, 2]) + A[3] * B[c, 3]
+    return R.reshape(16)
+
+
+def _glm_mat4_vec(M: np.ndarray, v: np.ndarray, w: float) -> np.ndarray:
+    """vec3(M * vec4(v, w)) for (n, 3) points, GLM's order: (m0*x + m1*y) + (m2*z + m3*w) (type_mat4x4.inl mat * vec)."""
+    m = M.astype(np.float32).reshape(4, 4)
+    x, y, z = (v[:, k:k + 1].astype(np.float32) for k in range(3))
+    r = (m[0][None, :] * x + m[1][None, :] * y) + (m[2][None, :] * z + m[3][None, :] * np.float32(w))
+    return np.ascontiguousarray(r[:, :3], np.float32)
+
+
+def load_gltf_scalp(path: str, mesh: int = 0) -> "ScalpMesh":
+    """Skinned scalp from a .gltf file (JSON with embedded base64 or side-by-side .bin buffers) the way the reference's loader
+    presents it to Hair::setup (src/memory/resources/mesh_data_manager.cc:755-880 + MeshData::setup, mesh_data.cc:384-436):
+    POSITION / NORMAL through the node's world matrix (w = 1 / w = 0), JOINTS_0 as integers, WEIGHTS_0 as floats, the index
+    list of all primitives of the mesh concatenated; vertices are then re-indexed in FIRST-APPEARANCE order over that index
+    list (every corner is the triple (i, i, i)), and joints / weights follow their vertex. The skin's joints, their inverse
+    bind matrices and the joints' global rest matrices come along for bh_dq_palette_from_matrices. Plain Python + numpy:
+    the reference reads the same file through cgltf; glb containers, sparse accessors and morph targets are not read."""
+    import base64, json
+    doc = json.load(open(path, "r"))
+    base = os.path.dirname(os.path.abspath(path))
+    blobs = []
+    for b in doc.get("buffers", []):
+        uri = b.get("uri", "")
+        if uri.startswith("data:"):
+            blobs.append(base64.b64decode(uri.split(",", 1)[1]))
+        else:
+            blobs.append(open(os.path.join(base, uri), "rb").read())
+
+    def accessor(i):
+        a = doc["accessors"][i]
+        if "sparse" in a:
+            raise ValueError("sparse accessors are not read (neither does the reference)")
+        bv = doc["bufferViews"][a["bufferView"]]
+        dt, width = np.dtype(_GLTF_COMPONENT[a["componentType"]]), _GLTF_WIDTH[a["type"]]
+        start = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+        stride = bv.get("byteStride", 0) or dt.itemsize * width
+        raw = np.frombuffer(blobs[bv["buffer"]], np.uint8, offset=start, count=(a["count"] - 1) * stride + dt.itemsize * width)
+        rows = np.lib.stride_tricks.as_strided(raw, shape=(a["count"], dt.itemsize * width), strides=(stride, 1))
+        out = np.ascontiguousarray(rows).view(dt).reshape(a["count"], width)
+        if a.get("normalized") and dt.kind in "iu":                          # cgltf_accessor_read_float normalises
+            out = np.maximum(out.astype(np.float32) / np.float32(np.iinfo(dt).max), np.float32(-1.0))
+        return out
+
+    def local_matrix(n):
+        if "matrix" in n:
+            return np.array(n["matrix"], np.float32)
+        t = np.array(n.get("translation", [0, 0, 0]), np.float32); q = np.array(n.get("rotation", [0, 0, 0, 1]), np.float32)
+        sc = np.array(n.get("scale", [1, 1, 1]), np.float32)
+        x, y, z, w = (np.float32(v) for v in q)
+        one, two = np.float32(1), np.float32(2)
+        R = np.array([[one - two * (y * y + z * z), two * (x * y + w * z), two * (x * z - w * y), 0],
+                      [two * (x * y - w * z), one - two * (x * x + z * z), two * (y * z + w * x), 0],
+                      [two * (x * z + w * y), two * (y * z - w * x), one - two * (x * x + y * y), 0], [0, 0, 0, 1]], np.float32)   # [column][row]
+        R[0, :3] *= sc[0]; R[1, :3] *= sc[1]; R[2, :3] *= sc[2]
+        R[3, :3] = t
+        return R.reshape(16)
+
+    nodes = doc.get("nodes", [])
+    parent = {c: i for i, n in enumerate(nodes) for c in n.get("children", [])}
+
+    def world_matrix(i):
+        M = local_matrix(nodes[i])
+        while i in parent:
+            i = parent[i]
+            M = _glm_mat4_mul(local_matrix(nodes[i]), M)
+        return M
+
+    node_id = next((i for i, n in enumerate(nodes) if n.get("mesh") == mesh), None)
+    world = world_matrix(node_id) if node_id is not None else np.eye(4, dtype=np.float32).reshape(16)
+    P, Nn, Jn, W, idx, last = [], [], [], [], [], 0
+    for prim in doc["meshes"][mesh]["primitives"]:
+        at = prim["attributes"]
+        pos = _glm_mat4_vec(world, accessor(at["POSITION"]).astype(np.float32), 1.0)
+        P.append(pos)
+        if "NORMAL" in at: Nn.append(_glm_mat4_vec(world, accessor(at["NORMAL"]).astype(np.float32), 0.0))
+        if "JOINTS_0" in at: Jn.append(accessor(at["JOINTS_0"]).astype(np.int32))
+        if "WEIGHTS_0" in at: W.append(accessor(at["WEIGHTS_0"]).astype(np.float32))
+        if "indices" not in prim:
+            raise ValueError("a primitive without indices: the reference loads no faces for it")
+        idx.append(accessor(prim["indices"]).reshape(-1).astype(np.int64) + last)
+        last += pos.shape[0]
+    P, idx = np.concatenate(P), np.concatenate(idx)
+    if not Nn:
+        raise ValueError("no NORMAL attribute: load the file's geometry through an OBJ, whose loader recalculates them")
+    Nn = np.concatenate(Nn)
+    # MeshData::setup: unique corner triples in first-appearance order (each corner is (i, i, i))
+    _, first = np.unique(idx, return_index=True)
+    order = idx[np.sort(first)]                                              # old vertex id of new vertex k
+    remap = np.full(P.shape[0], -1, np.int64); remap[order] = np.arange(order.size)
+    m = ScalpMesh(np.ascontiguousarray(P[order]), np.ascontiguousarray(Nn[order]), remap[idx].astype(np.int32).reshape(-1, 3))
+    if Jn and W:
+        m.joints, m.weights = np.ascontiguousarray(np.concatenate(Jn)[order]), np.ascontiguousarray(np.concatenate(W)[order])
+    skin_id = nodes[node_id].get("skin") if node_id is not None else None
+    if skin_id is not None:
+        skin = doc["skins"][skin_id]
+        m.joint_nodes = list(skin["joints"])
+        m.inverse_bind = np.ascontiguousarray(accessor(skin["inverseBindMatrices"]).astype(np.float32)) if "inverseBindMatrices" in skin \
+            else np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(m.joint_nodes), 1))
+        m.joint_rest_global = np.stack([world_matrix(j) for j in m.joint_nodes]).astype(np.float32)
+    return m
 
 
 def load_obj_scalp(path: str) -> "ScalpMesh":

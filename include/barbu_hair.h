@@ -115,8 +115,9 @@ int  bh_sphere_scalp_triangles(int rows, int cols, int32_t* tri_indices);
 
 /* ---- scalp input: the reference's OBJ reading rules (mesh_data_manager.cc:69-223) and vertex re-indexing
  * (mesh_data.cc:384-406): one root per unique (v, vt, vn) corner triple in first-appearance order, quads split as
- * (x, y, z), (z, w, x). Outputs are malloc'ed: release each with bh_free. A file without `vn` lines is refused with
- * BH_ERR_UNSUPPORTED (the reference would synthesise per-corner normals). Host only, no device needed. */
+ * (x, y, z), (z, w, x). A file without `vn` lines gets the normals RawMeshData::recalculateNormals would make
+ * (raw_mesh_file.cc:11-50): one per face corner, hence 3 roots per triangle. As in the reference a last line that does not
+ * end in '\n' is not read. Outputs are malloc'ed: release each with bh_free. Host only, no device needed. */
 int  bh_load_obj_scalp(const char* path, float** root_pos3, float** root_nrm3, int64_t* nvertices,
                        int32_t** tri_indices, int64_t* nfaces);
 void bh_free(void* ptr);
@@ -159,6 +160,11 @@ int  bh_selftest_math(int device, uint64_t* mismatches);
  * validated: negative ones are refused by bh_set_skin, ones >= njoints by bh_skin_roots (BH_ERR_INVALID). */
 int  bh_set_skin(bh_sim* sim, const float* rest_root_pos3, const int32_t* joints4, const float* weights3);
 int  bh_skin_roots(bh_sim* sim, const float* dq_palette, int njoints);
+/* The palette as the reference's animation system makes it (SkeletonController::generate_skinning_datas,
+ * src/fx/animation/skeleton_controller.cc:248-265): per joint global_pose * inverse_bind, its top three rows as the 3x4
+ * skinning matrix, glm::dualquat of that. Matrices in GLM's layout: 16 floats, column-major. dq_palette: njoints x 8 floats
+ * (real xyzw, dual xyzw) — the argument of bh_skin_roots. Host only, bit-identical to the reference's host code. */
+int  bh_dq_palette_from_matrices(const float* global_pose16, const float* inverse_bind16, int njoints, float* dq_palette);
 
 /* ---- next stage: the tess-stream pass of Hair::render (hair.cc:141-173) on the device ------------ */
 /* Interpolated render strands as the GL_LINES vertex stream (xyz, relPos) that glDrawTransformFeedback consumes:

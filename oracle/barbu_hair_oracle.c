@@ -461,3 +461,73 @@ void bho_tess_stream(const float* pos4, const float* tan4, const int32_t* patch_
       }
     }
 }
+
+/* RawMeshData::recalculateNormals (src/utils/raw_mesh_file.cc:11-50), the path MeshData::setup takes for a mesh that came
+ * without normals (src/memory/resources/mesh_data.cc:366-372): per face n = normalize(cross(v2 - v1, v3 - v2)) added,
+ * unweighted, to its three vertices (l.14-32); every vertex sum normalised (l.34-36); then EVERY corner gets a normal
+ * entry of its own, a copy of its vertex normal (l.38-49) — so the re-indexing of mesh_data.cc:384-406 finds 3 * F unique
+ * (v, vt, vn) triples: one hair root per face corner. GLM: cross (func_geometric.inl:74-77), dot = (x*x + y*y) + z*z
+ * (l.52-53), normalize = v * inversesqrt(dot) (l.88), inversesqrt = 1 / sqrt (func_exponential.inl:135-139).
+ * corner_v: 3 * nfaces zero-based position indices; nrm3_corner: 3 * nfaces normals. */
+void bho_recalc_normals(const float* pos3, int64_t nverts, const int32_t* corner_v, int64_t nfaces, float* nrm3_corner) {
+  float* acc = (float*)calloc((size_t)(nverts > 0 ? nverts : 1) * 3, sizeof(float));
+  for (int64_t f = 0; f < nfaces; ++f) {
+    const int32_t i1 = corner_v[3 * f], i2 = corner_v[3 * f + 1], i3 = corner_v[3 * f + 2];
+    const float *v1 = pos3 + 3 * (size_t)i1, *v2 = pos3 + 3 * (size_t)i2, *v3 = pos3 + 3 * (size_t)i3;
+    const float u[3] = { v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2] };
+    const float v[3] = { v3[0] - v2[0], v3[1] - v2[1], v3[2] - v2[2] };
+    const float c[3] = { u[1] * v[2] - v[1] * u[2], u[2] * v[0] - v[2] * u[0], u[0] * v[1] - v[0] * u[1] };
+    const float inv = inversesqrt1(dot3(c, c));
+    const int32_t ids[3] = { i1, i2, i3 };
+    for (int k = 0; k < 3; ++k)
+      for (int a = 0; a < 3; ++a) acc[3 * (size_t)ids[k] + a] += c[a] * inv;
+  }
+  for (int64_t i = 0; i < nverts; ++i) {
+    float* n = acc + 3 * (size_t)i;
+    const float inv = inversesqrt1(dot3(n, n));
+    n[0] *= inv; n[1] *= inv; n[2] *= inv;
+  }
+  for (int64_t q = 0; q < 3 * nfaces; ++q)
+    for (int a = 0; a < 3; ++a) nrm3_corner[3 * q + a] = acc[3 * (size_t)corner_v[q] + a];
+  free(acc);
+}
+
+/* SkeletonController::generate_skinning_datas (src/fx/animation/skeleton_controller.cc:248-265): per joint
+ * skin = global_pose * inverse_bind (GLM mat4 product, type_mat4x4.inl:643-646: ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per column),
+ * the 3x4 skinning matrix is the first three columns of its transpose (l.255), and the dual quaternion is
+ * glm::dualquat(mat3x4) = dualquat_cast (gtx/dual_quaternion.inl:303-351): rotation by the largest-diagonal branch, then
+ * dual = 0.5 * t * real spelled out. Matrices are GLM's: 16 floats, column-major. dq8: (real xyzw, dual xyzw) per joint —
+ * the two RGBA32F texels per joint inc_skinning.glsl:37-52 fetches. */
+void bho_dq_palette_from_matrices(const float* global_pose16, const float* inverse_bind16, int njoints, float* dq8) {
+  for (int j = 0; j < njoints; ++j) {
+    const float* A = global_pose16 + 16 * (size_t)j; const float* B = inverse_bind16 + 16 * (size_t)j;
+    float M[4][4];                                            /* M[col][row] */
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r)
+        M[c][r] = ((A[0 * 4 + r] * B[c * 4 + 0] + A[1 * 4 + r] * B[c * 4 + 1]) + A[2 * 4 + r] * B[c * 4 + 2]) + A[3 * 4 + r] * B[c * 4 + 3];
+    float x[3][4];                                            /* x[c] = column c of transpose(M) = row c of M */
+    for (int c = 0; c < 3; ++c)
+      for (int k = 0; k < 4; ++k) x[c][k] = M[k][c];
+    float q[4];                                               /* real: x y z w */
+    const float trace = x[0][0] + x[1][1] + x[2][2];
+    if (trace > 0.0f) {
+      const float r = sqrtf(1.0f + trace), invr = 0.5f / r;
+      q[3] = 0.5f * r; q[0] = (x[2][1] - x[1][2]) * invr; q[1] = (x[0][2] - x[2][0]) * invr; q[2] = (x[1][0] - x[0][1]) * invr;
+    } else if (x[0][0] > x[1][1] && x[0][0] > x[2][2]) {
+      const float r = sqrtf(1.0f + x[0][0] - x[1][1] - x[2][2]), invr = 0.5f / r;
+      q[0] = 0.5f * r; q[1] = (x[1][0] + x[0][1]) * invr; q[2] = (x[0][2] + x[2][0]) * invr; q[3] = (x[2][1] - x[1][2]) * invr;
+    } else if (x[1][1] > x[2][2]) {
+      const float r = sqrtf(1.0f + x[1][1] - x[0][0] - x[2][2]), invr = 0.5f / r;
+      q[0] = (x[1][0] + x[0][1]) * invr; q[1] = 0.5f * r; q[2] = (x[2][1] + x[1][2]) * invr; q[3] = (x[0][2] - x[2][0]) * invr;
+    } else {
+      const float r = sqrtf(1.0f + x[2][2] - x[0][0] - x[1][1]), invr = 0.5f / r;
+      q[0] = (x[0][2] + x[2][0]) * invr; q[1] = (x[2][1] + x[1][2]) * invr; q[2] = 0.5f * r; q[3] = (x[1][0] - x[0][1]) * invr;
+    }
+    float* o = dq8 + 8 * (size_t)j;
+    o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
+    o[4] = 0.5f * (x[0][3] * q[3] + x[1][3] * q[2] - x[2][3] * q[1]);
+    o[5] = 0.5f * (-x[0][3] * q[2] + x[1][3] * q[3] + x[2][3] * q[0]);
+    o[6] = 0.5f * (x[0][3] * q[1] - x[1][3] * q[0] + x[2][3] * q[3]);
+    o[7] = -0.5f * (x[0][3] * q[0] + x[1][3] * q[1] + x[2][3] * q[2]);
+  }
+}

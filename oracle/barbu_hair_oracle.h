@@ -87,6 +87,10 @@ void bho_skin_roots_dq(const float* rest_pos3, const float* rest_nrm3, const int
                        float* out_pos3, float* out_nrm3);
 
 /* FNV-1a 64 over raw bytes — "checksum of checksums" helper for full-size property tests. */
+/* RawMeshData::recalculateNormals (raw_mesh_file.cc:11-50): one normal per face corner for a scalp that came without. */
+void bho_recalc_normals(const float* pos3, int64_t nverts, const int32_t* corner_v, int64_t nfaces, float* nrm3_corner);
+/* generate_skinning_datas (skeleton_controller.cc:248-265): global pose x inverse bind -> glm::dualquat(mat3x4) per joint. */
+void bho_dq_palette_from_matrices(const float* global_pose16, const float* inverse_bind16, int njoints, float* dq8);
 uint64_t bho_fnv1a64(const void* data, uint64_t nbytes);
 
 /* Tess-stream stage (src/shaders/hair/02_tess_stream, hair.cc:141-173): interpolated render strands as GL_LINES

@@ -42,6 +42,9 @@ What it produces
   _ref/hair_init_simulation.gen.inc   body of Hair::init_simulation, src/fx/hair.cc:236-328
                                       (up to, not including, the GL buffer creation).
   _ref/hair_init_mesh.gen.inc         element loop of Hair::init_mesh, src/fx/hair.cc:397-409.
+  _ref/raw_recalc_normals.gen.inc     RawMeshData::recalculateNormals, src/utils/raw_mesh_file.cc:11-50 (scalps without normals).
+  _ref/generate_skinning_datas.gen.inc  SkeletonController::generate_skinning_datas, src/fx/animation/skeleton_controller.cc:248-265
+                                      (skinning matrices -> dual-quaternion palette).
 """
 import os
 import re
@@ -170,6 +173,16 @@ def gen_host():
     mesh = slice_lines("src/fx/hair.cc", 397, 409)
     assert "mesh_.patchsize = 6;" in mesh and "elements[idx++] = e + 1;" in mesh, "hair.cc moved; re-pin line numbers"
     open(os.path.join(OUT, "hair_init_mesh.gen.inc"), "w").write(mesh)
+    # RawMeshData::recalculateNormals, src/utils/raw_mesh_file.cc:11-50 (the whole member function definition)
+    rn = slice_lines("src/utils/raw_mesh_file.cc", 11, 50)
+    assert rn.startswith("void RawMeshData::recalculateNormals() {") and rn.rstrip().endswith("}") and "face.z = static_cast<uint32_t>(normals.size());" in rn, \
+        "raw_mesh_file.cc moved; re-pin line numbers"
+    open(os.path.join(OUT, "raw_recalc_normals.gen.inc"), "w").write(rn)
+    # SkeletonController::generate_skinning_datas, src/fx/animation/skeleton_controller.cc:248-265
+    gs = slice_lines("src/fx/animation/skeleton_controller.cc", 248, 265)
+    assert gs.startswith("void SkeletonController::generate_skinning_datas(") and gs.rstrip().endswith("}") and \
+        "glm::dualquat(skinning_matrices_[i])" in gs, "skeleton_controller.cc moved; re-pin line numbers"
+    open(os.path.join(OUT, "generate_skinning_datas.gen.inc"), "w").write(gs)
 
 
 if __name__ == "__main__":

@@ -185,6 +185,37 @@ def ref_patch_indices(tri, nstrands: int, nverts: int) -> np.ndarray:
     return out
 
 
+def recalc_normals(pos3, corner_v) -> np.ndarray:
+    """RawMeshData::recalculateNormals (raw_mesh_file.cc:11-50): one normal per face corner. corner_v: (F, 3) zero-based."""
+    pos3 = np.ascontiguousarray(pos3, np.float32).reshape(-1, 3); corner_v = np.ascontiguousarray(corner_v, np.int32).reshape(-1, 3)
+    out = np.empty((corner_v.size, 3), np.float32)
+    oracle().bho_recalc_normals(_p(pos3), C.c_int64(pos3.shape[0]), _p(corner_v), C.c_int64(corner_v.shape[0]), _p(out))
+    return out
+
+
+def ref_recalc_normals(pos3, corner_v):
+    """The reference's own function (oracle/_ref host harness). Returns (normals per corner (3F, 3), normal index per corner)."""
+    pos3 = np.ascontiguousarray(pos3, np.float32).reshape(-1, 3); corner_v = np.ascontiguousarray(corner_v, np.int32).reshape(-1, 3)
+    out = np.empty((corner_v.size, 3), np.float32); idx = np.empty(corner_v.size, np.int32)
+    _ref("host", 4).ref_host_recalc_normals(_p(pos3), C.c_int64(pos3.shape[0]), _p(corner_v), C.c_int64(corner_v.shape[0]), _p(out), _p(idx))
+    return out, idx
+
+
+def dq_palette_from_matrices(global_pose, inverse_bind) -> np.ndarray:
+    """generate_skinning_datas (skeleton_controller.cc:248-265). Matrices (J, 16) in GLM's column-major layout -> (J, 8)."""
+    A = np.ascontiguousarray(global_pose, np.float32).reshape(-1, 16); B = np.ascontiguousarray(inverse_bind, np.float32).reshape(-1, 16)
+    out = np.empty((A.shape[0], 8), np.float32)
+    oracle().bho_dq_palette_from_matrices(_p(A), _p(B), C.c_int(A.shape[0]), _p(out))
+    return out
+
+
+def ref_dq_palette_from_matrices(global_pose, inverse_bind) -> np.ndarray:
+    A = np.ascontiguousarray(global_pose, np.float32).reshape(-1, 16); B = np.ascontiguousarray(inverse_bind, np.float32).reshape(-1, 16)
+    out = np.empty((A.shape[0], 8), np.float32)
+    _ref("host", 4).ref_host_dq_palette(_p(A), _p(B), C.c_int(A.shape[0]), _p(out))
+    return out
+
+
 def ref_simplex2(x: float, y: float) -> float:
     return float(_ref("host", 4).ref_host_simplex2(x, y))
 
@@ -279,6 +310,12 @@ def obj_scalp(path: str):
             corners += cs[:3]
             if len(cs) == 4 and cs[3][0] > 0:
                 corners += [cs[2], cs[3], cs[0]]
+    if not nrm:
+        # MeshData::setup -> RawMeshData::recalculateNormals (mesh_data.cc:366-372, raw_mesh_file.cc:11-50): every corner gets
+        # a normal entry of its own, so all 3 * F corner triples are unique
+        cv = np.array([c[0] - 1 for c in corners], np.int32).reshape(-1, 3)
+        nrm = [list(x) for x in recalc_normals(np.array(pos, np.float32), cv)]
+        corners = [(v, t, q + 1) for q, (v, t, _) in enumerate(corners)]
     seen, uniq, idx = {}, [], []
     for v, t, n in corners:
         key = (v - 1, t - 1, n - 1)

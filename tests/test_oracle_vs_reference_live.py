@@ -191,3 +191,52 @@ def test_dq_skinning_bit_exact_vs_reference_shader(seed):
     assert_bit_equal(gp, rp, "skinned positions")
     assert_bit_equal(gn, rn, "skinned normals")
     assert np.array_equal(gp[0], pos[0]) and np.array_equal(gp[1], pos[1])      # weights.x <= Epsilon(): untouched
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_recalculated_normals_bit_exact_vs_reference_host_code(seed):
+    """Scalps without normals: bho_recalc_normals == RawMeshData::recalculateNormals (raw_mesh_file.cc:11-50, compiled here
+    from the reference source) on random triangle soups, including zero-area faces (normalize(0): NaN by the reference's own
+    arithmetic, which then poisons the three vertex sums), faces that repeat a vertex, and vertices no face uses."""
+    if not po.ref_available(4):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(500 + seed)
+    nv, nf = 60 + 40 * seed, 150 + 100 * seed
+    pos = (rng.standard_normal((nv, 3)) * [1.0, 1e-3, 1e4][seed]).astype(np.float32)
+    tri = rng.integers(0, nv - 3, (nf, 3)).astype(np.int32)                 # the last three vertices stay unused: 0 / 0
+    tri[5] = [7, 7, 9]                                                       # a repeated vertex: zero-area face
+    pos[11] = pos[12]; tri[6] = [11, 12, 13]                                 # coincident positions: zero-area face
+    want, idx = po.ref_recalc_normals(pos, tri)
+    assert idx.tolist() == list(range(3 * nf)), "every corner gets a normal entry of its own, in corner order"
+    got = po.recalc_normals(pos, tri)
+    assert_bit_equal(got, want, "per-corner normals")
+    assert np.isnan(want).any() and np.isfinite(want).any()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_dq_palette_bit_exact_vs_reference_host_code(seed):
+    """bho_dq_palette_from_matrices == SkeletonController::generate_skinning_datas + glm::dualquat(mat3x4)
+    (skeleton_controller.cc:248-265, gtx/dual_quaternion.inl:303-351; compiled here from the reference sources) on random
+    joints: rigid, scaled / sheared (not a rotation: the formula still has to match), near the branch boundaries of the
+    rotation extraction (trace ~ 0, equal diagonal entries), and with special values."""
+    if not po.ref_available(4):
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    rng = np.random.default_rng(900 + seed)
+    J = 256
+    G = rng.standard_normal((J, 16)).astype(np.float32); B = rng.standard_normal((J, 16)).astype(np.float32)
+    if seed == 0:                                                            # rigid transforms
+        for M in (G, B):
+            for j in range(J):
+                q = rng.standard_normal(4); x, y, z, w = q / np.linalg.norm(q)
+                R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w), 0], [2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w), 0],
+                              [2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y), 0], [*rng.standard_normal(3), 1]], np.float32)
+                M[j] = R.reshape(16)
+    if seed == 2:                                                            # branch boundaries: inverse bind = identity, crafted diagonals
+        B[:] = np.eye(4, dtype=np.float32).reshape(16)
+        G[:, 0], G[:, 5], G[:, 10] = 0.5, -0.25, -0.25                       # trace == 0 exactly -> second branch
+        G[64:128, 5] = 0.5                                                   # m00 == m11: neither of the first two diagonal branches
+        G[128:192, 10] = 0.5
+        G[192:, 0] = -1.0; G[192:, 5] = -1.0; G[192:, 10] = -1.0             # sqrt(1 + m22 - m00 - m11) = sqrt(2)
+    if seed == 3:
+        G[5, 0] = np.inf; G[6, 3] = np.nan; B[7] = 0.0; G[8] = 0.0           # r = 0 -> 0.5 / 0
+    assert_bit_equal(po.dq_palette_from_matrices(G, B), po.ref_dq_palette_from_matrices(G, B), "dual-quaternion palette")

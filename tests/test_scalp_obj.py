@@ -64,8 +64,8 @@ def test_obj_only_normals_and_errors(tmp_path):
     assert (m.nvertices, m.nfaces) == (3, 1)
     assert_bit_equal(m.positions, po.obj_scalp(path)[0])
     with pytest.raises(bb.BarbuHairError) as e:
-        bb.load_obj_scalp(write(tmp_path, "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", "nonormals.obj"))
-    assert e.value.code == hair.BH_ERR_UNSUPPORTED
+        bb.load_obj_scalp(write(tmp_path, "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4\n", "nonormals_badindex.obj"))
+    assert e.value.code == hair.BH_ERR_INVALID
     with pytest.raises(bb.BarbuHairError) as e:
         bb.load_obj_scalp(str(tmp_path / "missing.obj"))
     assert e.value.code == hair.BH_ERR_INVALID
@@ -74,6 +74,52 @@ def test_obj_only_normals_and_errors(tmp_path):
     h = bb.Hair()
     h.setup(str(tmp_path / "missing.obj"))           # Hair::setup with an unknown resource id: log + uninitialised
     assert not h.initialized() and "not found" in h.log[-1]
+
+
+def _grid_obj(n, with_vt, quads, seed=0):
+    """An n x n height-field patch without `vn` lines: quads or triangles, optionally with texture coordinates."""
+    rng = np.random.default_rng(seed)
+    lines = ["# scalp without normals", "o patch"]
+    for r in range(n):
+        for c in range(n):
+            lines.append(f"v {c / (n - 1):.6f} {0.2 * np.sin(3.0 * r / n) + 0.01 * rng.standard_normal():.6f} {r / (n - 1):.6f}")
+    if with_vt:
+        for r in range(n):
+            for c in range(n):
+                lines.append(f"vt {c / (n - 1):.4f} {r / (n - 1):.4f}")
+    vid = lambda r, c: r * n + c + 1
+    fmt = (lambda v: f"{v}/{v}") if with_vt else (lambda v: f"{v}")
+    for r in range(n - 1):
+        for c in range(n - 1):
+            a, b, d, e = vid(r, c), vid(r + 1, c), vid(r + 1, c + 1), vid(r, c + 1)
+            if quads: lines.append("f " + " ".join(fmt(v) for v in (a, b, d, e)))
+            else: lines += ["f " + " ".join(fmt(v) for v in (a, b, e)), "f " + " ".join(fmt(v) for v in (e, b, d))]
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("with_vt,quads", [(False, False), (False, True), (True, False), (True, True)])
+def test_obj_without_normals_gets_the_reference_recalculated_normals(tmp_path, with_vt, quads):
+    """A scalp file without `vn` lines: the normals RawMeshData::recalculateNormals makes (raw_mesh_file.cc:11-50; the oracle's
+    restatement is pinned to that source in test_oracle_vs_reference_live.py), one per face corner — so 3 roots per triangle
+    (mesh_data.cc:384-406 finds every corner triple unique), in corner order."""
+    n = 9
+    path = write(tmp_path, _grid_obj(n, with_vt, quads), "nonormals.obj")
+    m = bb.load_obj_scalp(path)
+    P, Nn, T = po.obj_scalp(path)
+    nf = 2 * (n - 1) * (n - 1)
+    assert (m.nvertices, m.nfaces) == (3 * nf, nf) and P.shape == (3 * nf, 3)
+    assert_bit_equal(m.positions, P, "root positions"); assert_bit_equal(m.normals, Nn, "recalculated normals"); assert_bit_equal(np.asarray(m.indices, np.int32).reshape(-1, 3), T)
+    assert np.asarray(m.indices).reshape(-1).tolist() == list(range(3 * nf))
+    ln = np.linalg.norm(m.normals.astype(np.float64), axis=1)
+    assert np.all(np.abs(ln - 1.0) < 1e-6), "unit normals"
+    # corners of one vertex share the vertex normal: an interior vertex of the triangle grid belongs to six faces
+    first = {}
+    for q, v in enumerate(np.round(m.positions, 6).tolist()):
+        first.setdefault(tuple(v), []).append(q)
+    assert max(len(v) for v in first.values()) == (6 if not quads else 6)
+    for qs in first.values():
+        for q in qs[1:]:
+            assert np.array_equal(m.normals[q].view(np.uint32), m.normals[qs[0]].view(np.uint32))
 
 
 @pytest.mark.skipif(not os.path.exists(ASSET), reason="reference tree not present (GPU box)")
