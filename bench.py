@@ -395,7 +395,7 @@ def run_gpu(args, rank, world, local_rank):
         sim.configure(math=math)
 
     # ---- end to end through the C ABI with HOST buffers (bh_step_host): H2D + 4 substeps + D2H per step ---
-    e2e_value, e2e_resident, e2e_steps = None, None, 0
+    e2e_value, e2e_resident, e2e_steps, e2e_copy_gbs, host_ceiling_gbs = None, None, 0, None, None
     if not args.no_e2e:
         hp, hv = bb.PinnedBuffer(4 * V), bb.PinnedBuffer(4 * V)
         p0, v0, _ = sim.download()
@@ -428,6 +428,29 @@ def run_gpu(args, rank, world, local_rank):
         if dist is not None:
             dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
         e2e_resident = world * V * SUBSTEPS * e2e_steps / float(t_res.item())
+        # What the box lets through at best: every rank copies its planes host->device and device->host at once, no kernel —
+        # the same pinned buffers, all ranks together. The e2e figure above can at most reach bytes / this rate
+        # (tools/pcie_probe.py, profiles/r02_pcie_probe.txt: the host side of these boxes saturates near 50 GB/s each way
+        # however many GPUs copy, so e2e stops scaling with N while the device-timed `value` does not).
+        dplane = torch.empty(8 * V, dtype=torch.float32, device="cuda")                # pos + vel: 32 B per vertex
+        hin = torch.from_numpy(hp.array); hout = torch.from_numpy(hv.array)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize(); barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                dplane[:4 * V].copy_(hin, non_blocking=True); dplane[:4 * V].copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hout.copy_(dplane[4 * V:], non_blocking=True); hout.copy_(dplane[4 * V:], non_blocking=True)
+            torch.cuda.synchronize()
+            t_c = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+            best = float(t_c.item()) if best is None else min(best, float(t_c.item()))
+        host_ceiling_gbs = world * 32.0 * V / best / 1e9                               # aggregate, each way, both ways busy
+        e2e_copy_gbs = world * 32.0 * V * e2e_steps / float(t_e2e.item()) / 1e9
+        del dplane
         hp.free(); hv.free()
 
     # ---- optional exchange step (N > 1): all-gather of the position plane to every rank, NCCL over NVLink ----------
@@ -473,7 +496,9 @@ def run_gpu(args, rank, world, local_rank):
                          "traffic": None, "kernel": kernel_names.get(kernel_kind, "?"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_VERTEX_PER_LAUNCH * V, "ms_per_launch": per_launch_s * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * V, "d2h_bytes_per_step": 32 * V,
-                    "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)"},
+                    "steps": e2e_steps, "api": "bh_step_host (pinned host pos+vel planes in and out every step)",
+                    "copy_gbs_each_way": e2e_copy_gbs, "host_ceiling_gbs": host_ceiling_gbs,
+                    "host_ceiling_note": "aggregate over all ranks, each way with both ways busy, same pinned buffers, no kernel, measured in this run"},
             "e2e_resident_state": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 16 * V,
                                    "steps": e2e_steps, "api": "bh_set_bounding_sphere + bh_step_readback(position plane): the reference's Hair::update "
                                    "call pattern, state resident on the device, positions read back to pinned host memory slice by slice behind the steps"},
