@@ -76,24 +76,36 @@ int ensure_roots(bh_sim* s) {
 }  // namespace
 
 namespace bh {
+int unmap_gl(bh_sim* s);
+bool shared_buffer(const bh_sim* s) { return s->gl_resource != nullptr || s->ext_buffer != nullptr; }
+
+// Buffer 0 lives in a buffer the renderer owns (a GL buffer object, hair.cc:371-389) or, same protocol, in a device
+// allocation of the caller: it is only OURS between map and unmap. Cleans up after itself: a failure leaves it unmapped.
 int map_gl(bh_sim* s) {
-  if (!s->gl_resource) return BH_OK;
-  BH_CUDA(cudaGraphicsMapResources(1, &s->gl_resource, s->stream));
-  void* ptr = nullptr; size_t bytes = 0;
-  BH_CUDA(cudaGraphicsResourceGetMappedPointer(&ptr, &bytes, s->gl_resource));
-  if (bytes < (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4)) return fail(BH_ERR_INVALID, "GL buffer smaller than 3 planes");
+  if (!shared_buffer(s)) return BH_OK;
+  if (s->shared_mapped) return fail(BH_ERR_INVALID, "shared buffer mapped twice");
+  void* ptr = s->ext_buffer; size_t bytes = s->ext_bytes;
+  if (s->gl_resource) {
+    BH_CUDA(cudaGraphicsMapResources(1, &s->gl_resource, s->stream));
+    const cudaError_t e = cudaGraphicsResourceGetMappedPointer(&ptr, &bytes, s->gl_resource);
+    if (e != cudaSuccess) { (void)cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream); (void)cudaGetLastError(); return fail(BH_ERR_CUDA, "cudaGraphicsResourceGetMappedPointer", e); }
+  }
+  s->shared_maps += 1; s->shared_mapped = true;
+  if (bytes < (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4)) { (void)unmap_gl(s); return fail(BH_ERR_INVALID, "shared buffer smaller than 3 planes"); }
   for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = static_cast<float4*>(ptr) + (size_t)p * s->nvertices;
   return BH_OK;
 }
 int unmap_gl(bh_sim* s) {
-  if (!s->gl_resource) return BH_OK;
-  BH_CUDA(cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream));
+  if (!shared_buffer(s) || !s->shared_mapped) return BH_OK;
+  s->shared_unmaps += 1; s->shared_mapped = false;
+  if (s->gl_resource) BH_CUDA(cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream));
   return BH_OK;
 }
 
 }  // namespace bh
 using bh::map_gl;
 using bh::unmap_gl;
+using bh::shared_buffer;
 
 namespace {
 // The sim's work moves to another stream: everything already queued on the old one comes first. All steps of a sim share one
@@ -122,9 +134,7 @@ cudaError_t launch_step_checked(bh_sim* s, const bh::StepArgs& a, cudaStream_t s
 // reports the unmap's own status on the regular path.
 struct GlMapped {
   bh_sim* s; int rc; bool mapped;
-  explicit GlMapped(bh_sim* sim) : s(sim), rc(map_gl(sim)), mapped(rc == BH_OK) {
-    if (!mapped && s->gl_resource) (void)cudaGraphicsUnmapResources(1, &s->gl_resource, s->stream), (void)cudaGetLastError();   // a map that failed half-way
-  }
+  explicit GlMapped(bh_sim* sim) : s(sim), rc(map_gl(sim)), mapped(rc == BH_OK) {}
   int done() { if (!mapped) return rc; mapped = false; return unmap_gl(s); }
   ~GlMapped() { if (mapped) { (void)unmap_gl(s); } }
   GlMapped(const GlMapped&) = delete; GlMapped& operator=(const GlMapped&) = delete;
@@ -262,7 +272,7 @@ int bh_download(bh_sim* s, float* pos4, float* vel4, float* tan4) {
 
 int bh_device_plane(bh_sim* s, int plane, void** device_ptr, uint64_t* nbytes) {
   if (!s || plane < 0 || plane >= BH_NUM_PLANES || !device_ptr) return fail(BH_ERR_INVALID, "bh_device_plane: bad argument");
-  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_device_plane: buffer 0 is a GL buffer (only mapped during a step)");
+  if (shared_buffer(s)) return fail(BH_ERR_UNSUPPORTED, "bh_device_plane: buffer 0 is a GL / caller-owned buffer (only ours during a call)");
   *device_ptr = s->planes[plane];
   if (nbytes) *nbytes = (uint64_t)s->nvertices * sizeof(float4);
   return BH_OK;
@@ -405,7 +415,7 @@ int bh_set_substep_fusion(bh_sim* s, int enabled) {
 int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
   if (!s || !pos4 || !vel4) return fail(BH_ERR_INVALID, "bh_step_host: NULL argument");
   if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step_host: substeps < 1");
-  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_step_host: buffer 0 is a GL buffer");
+  if (shared_buffer(s)) return fail(BH_ERR_UNSUPPORTED, "bh_step_host: buffer 0 is a GL / caller-owned buffer");
   DeviceGuard g(s->device);
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   // Strands are independent, so a slice of strands can be uploaded, stepped `substeps` times and downloaded while its
@@ -468,7 +478,7 @@ int bh_step_readback(bh_sim* s, float dt, int substeps, float* pos4) {
   if (!s || !pos4) return fail(BH_ERR_INVALID, "bh_step_readback: NULL argument");
   if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_step_readback: no strand state (call bh_upload / bh_init_* first)");
   if (substeps < 1) return fail(BH_ERR_INVALID, "bh_step_readback: substeps < 1");
-  if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_step_readback: buffer 0 is a GL buffer (the renderer reads it in place)");
+  if (shared_buffer(s)) return fail(BH_ERR_UNSUPPORTED, "bh_step_readback: buffer 0 is a GL / caller-owned buffer (the renderer reads it in place)");
   DeviceGuard g(s->device);
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   // The reference's frame: uniforms in, Hair::update, positions out (hair.cc:89-125 + the consumer of buffer 0). Strands are
@@ -632,31 +642,53 @@ int bh_tess_device_buffer(bh_sim* s, void** device_ptr, int64_t* count) {
   return BH_OK;
 }
 
+namespace {
+// Second half of a registration, common to both kinds of shared buffer: move the current state into it so that the VAO of
+// hair.cc:371-389 (or the caller) sees it; on any failure give the buffer back and keep stepping our own.
+int adopt_shared_buffer(bh_sim* s, const char* what) {
+  float4* own[BH_NUM_PLANES] = { s->buffer0, s->buffer0 + s->nvertices, s->buffer0 + 2 * s->nvertices };
+  auto give_back = [&] {
+    if (s->gl_resource) { cudaGraphicsUnregisterResource(s->gl_resource); s->gl_resource = nullptr; }
+    s->ext_buffer = nullptr; s->ext_bytes = 0;
+    for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p];
+  };
+  int rc = map_gl(s);
+  if (rc) { give_back(); return rc; }
+  const cudaError_t e = cudaMemcpyAsync(s->planes[0], s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+  rc = unmap_gl(s);
+  if (e != cudaSuccess || rc) { (void)cudaGetLastError(); give_back(); return e != cudaSuccess ? fail(BH_ERR_CUDA, what, e) : rc; }
+  return BH_OK;
+}
+}  // namespace
+
 int bh_register_gl_buffer(bh_sim* s, unsigned int gl_buffer) {
   if (!s) return fail(BH_ERR_INVALID, "bh_register_gl_buffer: sim is NULL");
-  if (s->gl_resource) return fail(BH_ERR_INVALID, "bh_register_gl_buffer: already registered");
+  if (shared_buffer(s)) return fail(BH_ERR_INVALID, "bh_register_gl_buffer: a buffer is already registered");
   DeviceGuard g(s->device);
   cudaGraphicsResource* res = nullptr;
   BH_CUDA(cudaGraphicsGLRegisterBuffer(&res, gl_buffer, 0 /* cudaGraphicsRegisterFlagsNone: read + write */));
   s->gl_resource = res;
-  // Move the current state into the GL buffer so the VAO of hair.cc:371-389 sees it.
-  float4* own[BH_NUM_PLANES] = { s->buffer0, s->buffer0 + s->nvertices, s->buffer0 + 2 * s->nvertices };
-  int rc = map_gl(s);
-  if (rc) { cudaGraphicsUnregisterResource(res); s->gl_resource = nullptr; for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p]; return rc; }
-  cudaError_t e = cudaMemcpyAsync(s->planes[0], s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
-  rc = unmap_gl(s);
-  if (e != cudaSuccess || rc) {                                             // the state never reached the GL buffer: keep stepping our own
+  return adopt_shared_buffer(s, "bh_register_gl_buffer: copy into the GL buffer");
+}
+
+int bh_register_device_buffer(bh_sim* s, void* device_ptr, uint64_t nbytes) {
+  if (!s || !device_ptr) return fail(BH_ERR_INVALID, "bh_register_device_buffer: NULL argument");
+  if (shared_buffer(s)) return fail(BH_ERR_INVALID, "bh_register_device_buffer: a buffer is already registered");
+  if (nbytes < (uint64_t)BH_NUM_PLANES * s->nvertices * sizeof(float4)) return fail(BH_ERR_INVALID, "bh_register_device_buffer: buffer smaller than 3 planes");
+  if (reinterpret_cast<uintptr_t>(device_ptr) % 128) return fail(BH_ERR_INVALID, "bh_register_device_buffer: the buffer must be 128-byte aligned (TMA tiles)");
+  DeviceGuard g(s->device);
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, device_ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != s->device) {
     (void)cudaGetLastError();
-    cudaGraphicsUnregisterResource(res); s->gl_resource = nullptr;
-    for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = own[p];
-    return e != cudaSuccess ? fail(BH_ERR_CUDA, "bh_register_gl_buffer: copy into GL buffer", e) : rc;
+    return fail(BH_ERR_INVALID, "bh_register_device_buffer: not a device allocation of the sim's GPU");
   }
-  return BH_OK;
+  s->ext_buffer = device_ptr; s->ext_bytes = (size_t)nbytes;
+  return adopt_shared_buffer(s, "bh_register_device_buffer: copy into the buffer");
 }
 
 int bh_unregister_gl_buffer(bh_sim* s) {
   if (!s) return fail(BH_ERR_INVALID, "bh_unregister_gl_buffer: sim is NULL");
-  if (!s->gl_resource) return BH_OK;
+  if (!shared_buffer(s)) return BH_OK;
   DeviceGuard g(s->device);
   int rc = map_gl(s);
   if (rc == BH_OK) {
@@ -664,9 +696,18 @@ int bh_unregister_gl_buffer(bh_sim* s) {
     unmap_gl(s);
     cudaStreamSynchronize(s->stream);
   }
-  cudaGraphicsUnregisterResource(s->gl_resource);
-  s->gl_resource = nullptr;
+  if (s->gl_resource) cudaGraphicsUnregisterResource(s->gl_resource);
+  s->gl_resource = nullptr; s->ext_buffer = nullptr; s->ext_bytes = 0;
   for (int p = 0; p < BH_NUM_PLANES; ++p) s->planes[p] = s->buffer0 + (size_t)p * s->nvertices;
+  return BH_OK;
+}
+int bh_unregister_device_buffer(bh_sim* s) { return bh_unregister_gl_buffer(s); }
+
+int bh_buffer_map_stats(const bh_sim* s, int64_t* maps, int64_t* unmaps, int* mapped_now) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_buffer_map_stats: sim is NULL");
+  if (maps) *maps = s->shared_maps;
+  if (unmaps) *unmaps = s->shared_unmaps;
+  if (mapped_now) *mapped_now = s->shared_mapped ? 1 : 0;
   return BH_OK;
 }
 

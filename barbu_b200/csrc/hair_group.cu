@@ -71,7 +71,7 @@ int gather_into(bh_group* g, int plane, float4* dst_plane, int dst_device, cudaS
   for (int q = 0; q < G; ++q) {
     bh_sim* s = g->shard[q];
     if (!s->initialized) return fail(BH_ERR_NOT_INITIALIZED, "bh_group_gather_plane: a shard has no strand state");
-    if (s->gl_resource) return fail(BH_ERR_UNSUPPORTED, "bh_group_gather_plane: shard buffers registered with GL one by one cannot be gathered");
+    if (s->gl_resource || s->ext_buffer) return fail(BH_ERR_UNSUPPORTED, "bh_group_gather_plane: shard buffers registered with GL one by one cannot be gathered");
     DeviceGuard d(s->device);
     const size_t off = (size_t)g->first[q] * g->nverts, bytes = (size_t)(g->first[q + 1] - g->first[q]) * g->nverts * sizeof(float4);
     BH_CUDA(cudaEventRecord(g->ev0[q], s->stream));

@@ -68,6 +68,12 @@ struct bh_sim {
   int64_t tess_out_cap = 0, tess_out_count = 0;
   // GL interop
   cudaGraphicsResource* gl_resource = nullptr;
+  // bh_register_device_buffer: a caller-owned device allocation in the GL buffer's role (same state machine: planes live
+  // there, every entry point brackets its work with map / unmap); and the bracket's bookkeeping for both kinds
+  void* ext_buffer = nullptr;
+  size_t ext_bytes = 0;
+  int64_t shared_maps = 0, shared_unmaps = 0;
+  bool shared_mapped = false;
   // state files / checksums (hair_state.cu)
   unsigned long long* checksum_words = nullptr;   // 2 device words
 };

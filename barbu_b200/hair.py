@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
     "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_dq_palette_from_matrices", "bh_register_gl_buffer",
-    "bh_unregister_gl_buffer", "bh_last_error", "bh_version",
+    "bh_unregister_gl_buffer", "bh_register_device_buffer", "bh_unregister_device_buffer", "bh_buffer_map_stats", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
     "bh_marschner_default_params", "bh_marschner_generate",
     "bh_group_create", "bh_group_destroy", "bh_group_size", "bh_group_shard", "bh_group_shard_range", "bh_group_set_params",
@@ -119,6 +119,9 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_set_substep_fusion": ([vp, C.c_int], C.c_int),
         "bh_step_readback": ([vp, f32, C.c_int, vp], C.c_int),
         "bh_dq_palette_from_matrices": ([vp, vp, C.c_int, vp], C.c_int),
+        "bh_register_device_buffer": ([vp, vp, C.c_uint64], C.c_int),
+        "bh_unregister_device_buffer": ([vp], C.c_int),
+        "bh_buffer_map_stats": ([vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
@@ -450,6 +453,19 @@ class HairSim:
 
     def unregister_gl_buffer(self):
         _check(self._lib.bh_unregister_gl_buffer(self._h))
+
+    def register_device_buffer(self, device_ptr: int, nbytes: int):
+        """Step in a device allocation the caller owns (the GL buffer's protocol without GL, bh_register_device_buffer)."""
+        _check(self._lib.bh_register_device_buffer(self._h, C.c_void_p(device_ptr), nbytes))
+
+    def unregister_device_buffer(self):
+        _check(self._lib.bh_unregister_device_buffer(self._h))
+
+    def buffer_map_stats(self):
+        """(maps, unmaps, mapped_now) of the registered GL / caller-owned buffer."""
+        m, u, n = C.c_int64(), C.c_int64(), C.c_int()
+        _check(self._lib.bh_buffer_map_stats(self._h, C.byref(m), C.byref(u), C.byref(n)))
+        return int(m.value), int(u.value), bool(n.value)
 
 
 class HairGroup:

@@ -273,6 +273,16 @@ int     bh_group_gather_to_gl(bh_group* group, unsigned plane_mask);
  * current GL context on the calling thread; returns BH_ERR_CUDA otherwise. */
 int  bh_register_gl_buffer(bh_sim* sim, unsigned int gl_buffer);
 int  bh_unregister_gl_buffer(bh_sim* sim);
+/* The same protocol for a device allocation the caller owns (another CUDA allocation, a Vulkan / D3D buffer imported through
+ * cudaImportExternalMemory, a slice of the renderer's arena): the state moves into it, every entry point brackets its work
+ * with the map / unmap pair exactly as for a GL buffer (with a plain allocation the pair only keeps the books), and
+ * bh_unregister_device_buffer moves the state back. `device_ptr`: >= 3 * V * 16 bytes on the sim's GPU, 128-byte aligned.
+ * This is also how the GL path's state machine is exercised where no GL context exists (tests/test_shared_buffer.py). */
+int  bh_register_device_buffer(bh_sim* sim, void* device_ptr, uint64_t nbytes);
+int  bh_unregister_device_buffer(bh_sim* sim);
+/* Map / unmap bookkeeping of the registered buffer (GL or caller-owned): calls so far and whether it is mapped right now —
+ * after any entry point has returned, successfully or not, maps == unmaps and mapped_now == 0. */
+int  bh_buffer_map_stats(const bh_sim* sim, int64_t* maps, int64_t* unmaps, int* mapped_now);
 
 const char* bh_last_error(void);     /* thread-local message of the last failing call */
 const char* bh_version(void);
