@@ -173,7 +173,7 @@ int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
   s->device = device; s->nstrands = nstrands; s->nverts = nverts; s->nvertices = nstrands * (int64_t)nverts;
   bh_default_params(&s->params);
   static const bool fuse_env = [] { const char* e = getenv("BH_SUBSTEP_FUSION"); return e && e[0] == '1'; }();   // tuning knob: default of bh_set_substep_fusion
-  s->fuse_substeps = fuse_env;
+  s->fuse_substeps = fuse_env ? 1 : 0;
   cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&s->tile_counters, sizeof(unsigned int) * 32 * (kHostPipeStreams + 1));
   if (e == cudaSuccess) {
@@ -385,7 +385,7 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
   static const bool zigzag = [] { const char* e = getenv("BH_NO_ZIGZAG"); return !(e && e[0] == '1'); }();
-  if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+  if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps, s->fuse_substeps == 2)) {
     // Frame-level fusion: the substeps of this frame as the passes of ONE launch (StepArgs::passes). Same arithmetic, same
     // order per strand, so the result is bit-identical to `substeps` launches; HBM sees the state once per frame.
     a.passes = substeps;
@@ -408,7 +408,8 @@ int bh_step(bh_sim* s, float dt, int substeps) {
 
 int bh_set_substep_fusion(bh_sim* s, int enabled) {
   if (!s) return fail(BH_ERR_INVALID, "bh_set_substep_fusion: sim is NULL");
-  s->fuse_substeps = enabled != 0;
+  if (enabled < 0 || enabled > 2) return fail(BH_ERR_INVALID, "bh_set_substep_fusion: 0 (off), 1 (where it pays) or 2 (always)");
+  s->fuse_substeps = enabled;
   return BH_OK;
 }
 
@@ -457,7 +458,7 @@ int bh_step_host(bh_sim* s, float dt, int substeps, float* pos4, float* vel4) {
     if (e == cudaSuccess) e = cudaEventRecord(uploaded, up);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(run, uploaded, 0);
     bh::StepArgs a = make_args(s, h, dP, dV, count);
-    if (e == cudaSuccess && s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+    if (e == cudaSuccess && s->fuse_substeps && bh::stream_fusion_eligible(a, substeps, s->fuse_substeps == 2)) {
       a.passes = substeps;                                                  // the substeps of the slice as passes of one launch
       e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1;
     } else {
@@ -505,7 +506,7 @@ int bh_step_readback(bh_sim* s, float dt, int substeps, float* pos4) {
     const size_t off = (size_t)first * s->nverts, bytes = (size_t)count * s->nverts * sizeof(float4);
     float4* dP = s->planes[BH_PLANE_POSITION] + off;
     bh::StepArgs a = make_args(s, h, dP, s->planes[BH_PLANE_VELOCITY] + off, count);
-    if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps)) {
+    if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps, s->fuse_substeps == 2)) {
       a.passes = substeps;
       e = launch_step_checked(s, a, run, s->tile_counters); s->launches += 1;
     } else {

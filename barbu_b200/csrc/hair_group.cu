@@ -210,6 +210,12 @@ int bh_group_step(bh_group* g, float dt, int substeps) {
   return BH_OK;
 }
 
+int bh_group_set_substep_fusion(bh_group* g, int enabled) {
+  if (!g) return fail(BH_ERR_INVALID, "bh_group_set_substep_fusion: group is NULL");
+  for (bh_sim* s : g->shard) { int rc = bh_set_substep_fusion(s, enabled); if (rc) return rc; }
+  return BH_OK;
+}
+
 int bh_group_synchronize(bh_group* g) {
   if (!g) return fail(BH_ERR_INVALID, "bh_group_synchronize: group is NULL");
   for (bh_sim* s : g->shard) { int rc = bh_synchronize(s); if (rc) return rc; }

@@ -59,7 +59,10 @@ int step_kernel_kind(const StepArgs& a);
 // hair_stream.cu
 bool stream_kernel_eligible(const StepArgs& a);
 // Whether `passes` consecutive steps of this shape can run as one fused launch of the streaming kernel (see StepArgs::passes).
-bool stream_fusion_eligible(const StepArgs& a, int passes);
+// `always` = false adds the question whether it pays: a group of tiles runs all passes on ONE warp, so on a shard with fewer
+// groups than the GPU has resident warps fusion trades parallelism for L2 reuse and launch overhead — measured
+// (tools/small_latency.py) it wins only when a group is a single tile (>= 25 vertices per strand) or there are >= 1024 groups.
+bool stream_fusion_eligible(const StepArgs& a, int passes, bool always = true);
 cudaError_t selftest_inversesqrt(unsigned long long* mismatches);
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 

@@ -896,12 +896,14 @@ cudaError_t launch_stream_t(const StepArgs& a, cudaStream_t stream, unsigned int
                       : launch_stream_tf<PM, ORIGIN, NS, CAPS, false>(a, stream, tile_counter, variant);
 }
 
-bool stream_fusion_eligible(const StepArgs& a, int passes) {
+bool stream_fusion_eligible(const StepArgs& a, int passes, bool always) {
   static const bool disabled = [] { const char* e = getenv("BH_NO_SUBSTEP_FUSION"); return e && e[0] == '1'; }();   // tuning knob
   if (disabled || passes < 2 || passes > 64 || !stream_kernel_eligible(a)) return false;   // the pass counter shares a word with the chunk index
   if (a.nverts == 4 && a.nstrands % 2) return false;                        // the odd last strand runs on the per-strand kernel: step by step
   const long long ntiles = ((a.nverts == 4 ? a.nstrands / 2 : a.nstrands) + 31) / 32;
-  return ntiles >= fusion_group_tiles(a.nverts);
+  const int gtiles = fusion_group_tiles(a.nverts);
+  if (ntiles < gtiles) return false;
+  return always || gtiles == 1 || ntiles / gtiles >= 1024;
 }
 
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
-    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
+    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_group_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_dq_palette_from_matrices", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_register_device_buffer", "bh_unregister_device_buffer", "bh_buffer_map_stats", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
@@ -122,6 +122,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_register_device_buffer": ([vp, vp, C.c_uint64], C.c_int),
         "bh_unregister_device_buffer": ([vp], C.c_int),
         "bh_buffer_map_stats": ([vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)], C.c_int),
+        "bh_group_set_substep_fusion": ([vp, C.c_int], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
@@ -311,9 +312,10 @@ class HairSim:
         _apply_param_keywords(p, kw)
         self.set_params(p)
 
-    def set_substep_fusion(self, enabled: bool):
-        """step(dt, k > 1) as k passes of ONE launch (tiles re-read from L2 between substeps); bit-identical results."""
-        _check(self._lib.bh_set_substep_fusion(self._h, 1 if enabled else 0))
+    def set_substep_fusion(self, enabled, always: bool = False):
+        """step(dt, k > 1) as k passes of ONE launch (tiles re-read from L2 between substeps); bit-identical results.
+        enabled: fuse where it pays (small shards keep their launches); always=True: wherever the shape allows it."""
+        _check(self._lib.bh_set_substep_fusion(self._h, (2 if always else 1) if enabled else 0))
 
     def set_bounding_sphere(self, sphere: Sequence[float]):
         _check(self._lib.bh_set_bounding_sphere(self._h, (C.c_float * 4)(*sphere)))
@@ -519,6 +521,10 @@ class HairGroup:
 
     def init_sphere_scalp(self, rows: int, cols: int, order: int = BH_SCALP_COLUMN_MAJOR, seed: int = 1234, maxlength: float = 0.5):
         _check(self._lib.bh_group_init_sphere_scalp(self._h, rows, cols, order, seed, maxlength))
+
+    def set_substep_fusion(self, enabled, always: bool = False):
+        """HairSim.set_substep_fusion on every shard."""
+        _check(self._lib.bh_group_set_substep_fusion(self._h, (2 if always else 1) if enabled else 0))
 
     def init_strands(self, root_pos3, root_nrm3, random_value, maxlength: float = 0.5):
         p, n, r = _f32(root_pos3, 3), _f32(root_nrm3, 3), _f32(random_value)

@@ -134,7 +134,10 @@ int  bh_step(bh_sim* sim, float dt, int substeps);
  * takes a group of tiles through all passes before it asks for more, so a pass re-reads from L2 what the previous one
  * stored, and HBM carries 64 B per vertex per frame instead of per substep. Per strand the operations and their order are
  * those of `substeps` separate launches: results are bit-identical. Shapes the streaming kernel does not take (nverts = 1,
- * iteration counts other than 8, fewer tiles than one group) silently keep one launch per substep. */
+ * iteration counts other than 8, fewer tiles than one group) silently keep one launch per substep.
+ * enabled: 0 off; 1 fuse where it pays (a group of tiles runs all its passes on one warp, so small shards — fewer than 1024
+ * groups of more than one tile, e.g. the reference's own 448 x 4 scalp — keep their launches and their parallelism);
+ * 2 fuse wherever the shape allows it (tests). */
 int  bh_set_substep_fusion(bh_sim* sim, int enabled);
 /* Same through HOST buffers: upload pos/vel, step, download pos/vel; copies are chunked and
  * overlapped with the kernels on internal streams. Buffers should be page-locked (bh_host_alloc). */
@@ -251,6 +254,7 @@ int     bh_group_init_strands(bh_group* group, const float* root_pos3, const flo
 int     bh_group_upload(bh_group* group, const float* pos4, const float* vel4, const float* tan4);   /* global planes */
 int     bh_group_download(bh_group* group, float* pos4, float* vel4, float* tan4);
 int     bh_group_step(bh_group* group, float dt, int substeps);                       /* Hair::update(dt); returns after the launches */
+int     bh_group_set_substep_fusion(bh_group* group, int enabled);                    /* bh_set_substep_fusion on every shard */
 int     bh_group_synchronize(bh_group* group);
 /* `frames` x bh_group_step between per-device CUDA events: ms_per_shard[g] (may be NULL) and their maximum — the frame
  * time of the job, measured on the devices. */

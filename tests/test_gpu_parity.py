@@ -804,7 +804,7 @@ def test_fused_substeps_bit_identical_to_separate_launches(S, N, k, math):
     for fuse in (False, True):
         with bb.HairSim(S, N) as sim:
             sim.configure(scale=1.45, sphere=SPHERE, math=math)
-            sim.set_substep_fusion(fuse)
+            sim.set_substep_fusion(fuse, always=True)
             sim.upload(pos, vel)
             l0 = sim.launch_count
             for _ in range(3):
@@ -836,7 +836,7 @@ def test_fused_substeps_full_size_bit_identical_and_capsules():
     for fuse in (False, True):
         with bb.HairSim(S, N) as sim:
             sim.configure(scale=1.45, sphere=SPHERE, math=bb.BH_MATH_EXACT)
-            sim.set_substep_fusion(fuse)
+            sim.set_substep_fusion(fuse, always=True)
             sim.init_sphere_scalp(rows, cols, 0, bb.random_values(1234, 0, S), order=bb.BH_SCALP_COLUMN_MAJOR)
             for _ in range(12):
                 sim.step(float(DT), 4)
@@ -859,7 +859,7 @@ def test_fused_substeps_full_size_bit_identical_and_capsules():
     outs = []
     for fuse in (False, True):
         with bb.HairSim(S, N) as sim:
-            sim.set_params(cfg); sim.set_substep_fusion(fuse); sim.upload(pos, vel)
+            sim.set_params(cfg); sim.set_substep_fusion(fuse, always=True); sim.upload(pos, vel)
             for _ in range(5):
                 sim.step(float(DT), 4)
             outs.append(sim.download()[:2])
@@ -874,7 +874,7 @@ def test_step_readback_equals_step_then_download(S, N, k, fuse):
     with bb.HairSim(S, N) as a, bb.HairSim(S, N) as b:
         for sim in (a, b):
             sim.configure(scale=1.45, sphere=SPHERE)
-            sim.set_substep_fusion(fuse)
+            sim.set_substep_fusion(fuse, always=True)
             sim.upload(pos, vel)
         out = bb.PinnedBuffer(4 * S * N)
         for _ in range(3):

@@ -72,10 +72,20 @@ def test_group_global_planes_upload_step_timed_download():
         grp.upload(pos, vel, tan)
         mx, per = grp.step_timed(float(DT), 1, 4)
         gp, gv, gt = grp.download()
+        # substep fusion on every shard: 3 substeps as 3 passes of one launch per shard, bit-identical
+        launches = grp.launch_count
+        grp.set_substep_fusion(True, always=True)
+        grp.step(float(DT), 3); grp.synchronize()
+        assert grp.launch_count - launches == 3, "one fused launch per shard"
+        fp, fv, _ = grp.download()
     assert len(per) == 3 and mx == max(per) and min(per) > 0.0
     for _ in range(4):
         po.step(pos, vel, S, N, par)
     assert_bit_equal(gp, pos); assert_bit_equal(gv, vel); assert_bit_equal(gt, tan)
+    par3 = po.default_params(dt=float(np.float32(DT) / np.float32(3)), scale=1.0, sphere=SPHERE)
+    for _ in range(3):
+        po.step(pos, vel, S, N, par3)
+    assert_bit_equal(fp, pos, "fused group step"); assert_bit_equal(fv, vel)
 
 
 @pytest.mark.gpu
