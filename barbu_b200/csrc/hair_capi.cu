@@ -175,6 +175,9 @@ int bh_create(bh_sim** out, int64_t nstrands, int nverts, int device) {
   static const bool fuse_env = [] { const char* e = getenv("BH_SUBSTEP_FUSION"); return e && e[0] == '1'; }();   // tuning knob: default of bh_set_substep_fusion
   s->fuse_substeps = fuse_env ? 1 : 0;
   cudaError_t e = cudaMalloc(&s->buffer0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
+  // defined contents from the start: a plane nobody uploaded (the tangents of a sim fed positions only) still travels in
+  // whole-buffer copies — state files, the move into a shared buffer — and reads as zeros there, not as stale memory
+  if (e == cudaSuccess) e = cudaMemset(s->buffer0, 0, (size_t)BH_NUM_PLANES * s->nvertices * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&s->tile_counters, sizeof(unsigned int) * 32 * (kHostPipeStreams + 1));
   if (e == cudaSuccess) {
     unsigned int words[32 * (kHostPipeStreams + 1)] = { 0 };
