@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbarbu_hair.so")
-SOURCES = ["hair_step.cu", "hair_stream.cu", "hair_gen.cu", "hair_tess.cu", "hair_state.cu", "hair_marschner.cu", "hair_capi.cu", "hair_group.cu", "hair_host.cc"]
+SOURCES = ["hair_step.cu", "hair_stream.cu", "hair_wave.cu", "hair_gen.cu", "hair_tess.cu", "hair_state.cu", "hair_marschner.cu", "hair_capi.cu", "hair_group.cu", "hair_host.cc"]
 HEADERS = ["hair_step.cuh", "hair_gen.cuh", "hair_math.cuh", "hair_collide.cuh", "hair_sim.cuh", os.path.join("..", "..", "include", "barbu_hair.h")]
 
 NVCC_FLAGS = [

@@ -43,6 +43,8 @@ using bh::kHostPipeStreams;
 
 namespace {
 
+constexpr int64_t kAutoLatencyVertices = 1 << 18;
+
 bh::StepArgs make_args(const bh_sim* s, float dt, float4* pos, float4* vel, int64_t nstrands) {
   const bh_params& p = s->params;
   bh::StepArgs a;
@@ -59,6 +61,9 @@ bh::StepArgs make_args(const bh_sim* s, float dt, float4* pos, float4* vel, int6
   a.r2 = p.sphere[3] * p.sphere[3];                  // radius * radius, cs:133
   a.use_drag = (p.drag != 0.0f) ? 1 : 0;
   a.keep = 1.0f - p.drag;
+  // small scalps: the latency-oriented kernel (hair_wave.cu). AUTO draws the line where the throughput kernels stop being
+  // latency-bound themselves (tools/small_latency.py: up to 2^18 vertices the wavefront kernel is the faster one)
+  a.prefer_latency = s->step_policy == BH_POLICY_LATENCY || (s->step_policy == BH_POLICY_AUTO && s->nvertices <= kAutoLatencyVertices);   // by the sim's size, not a slice's
   a.ncaps = p.ncapsules;
   for (int q = 0; q < p.ncapsules && q < bh::kMaxCapsules; ++q) {
     const bh_capsule& c = p.capsules[q];
@@ -388,6 +393,14 @@ int bh_step(bh_sim* s, float dt, int substeps) {
   const float h = (substeps == 1) ? dt : dt / static_cast<float>(substeps);
   bh::StepArgs a = make_args(s, h, s->planes[BH_PLANE_POSITION], s->planes[BH_PLANE_VELOCITY], s->nstrands);
   static const bool zigzag = [] { const char* e = getenv("BH_NO_ZIGZAG"); return !(e && e[0] == '1'); }();
+  if (a.prefer_latency && bh::wave_kernel_eligible(a)) {
+    // latency-oriented kernel: a warp owns its strands outright, so the substeps of the frame are simply passes of one launch
+    a.passes = substeps;
+    BH_CUDA(launch_step_checked(s, a, s->stream, s->tile_counters + 32 * kHostPipeStreams));
+    s->launches += 1;
+    s->step_launches += 1;
+    return gl.done();
+  }
   if (s->fuse_substeps && bh::stream_fusion_eligible(a, substeps, s->fuse_substeps == 2)) {
     // Frame-level fusion: the substeps of this frame as the passes of ONE launch (StepArgs::passes). Same arithmetic, same
     // order per strand, so the result is bit-identical to `substeps` launches; HBM sees the state once per frame.
@@ -407,6 +420,13 @@ int bh_step(bh_sim* s, float dt, int substeps) {
     s->step_launches += 1;
   }
   return gl.done();
+}
+
+int bh_set_step_policy(bh_sim* s, int policy) {
+  if (!s) return fail(BH_ERR_INVALID, "bh_set_step_policy: sim is NULL");
+  if (policy != BH_POLICY_THROUGHPUT && policy != BH_POLICY_LATENCY && policy != BH_POLICY_AUTO) return fail(BH_ERR_INVALID, "bh_set_step_policy: unknown policy");
+  s->step_policy = policy;
+  return BH_OK;
 }
 
 int bh_set_substep_fusion(bh_sim* s, int enabled) {

@@ -45,6 +45,7 @@ struct bh_sim {
   cudaStream_t pipe[bh::kHostPipeStreams] = { nullptr, nullptr, nullptr, nullptr };
   bh_params params;
   bool initialized = false;              // Hair::initialized(): state present
+  int step_policy = 0;                   // bh_set_step_policy: BH_POLICY_THROUGHPUT / LATENCY / AUTO
   int fuse_substeps = 0;                 // bh_set_substep_fusion: 0 off, 1 where it pays, 2 wherever the shape allows it
   int64_t launches = 0;
   int64_t step_launches = 0;             // launches of bh_step alone: parity = tile direction of the next one

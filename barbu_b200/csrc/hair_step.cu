@@ -403,12 +403,14 @@ cudaError_t launch_t(const StepArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int step_kernel_kind(const StepArgs& a) {
+  if (a.prefer_latency && wave_kernel_eligible(a)) return 3;
   if (stream_kernel_eligible(a)) return 0;
   return a.iterations == kChunk && a.r2 <= 1.8446744073709551616e19f ? 1 : 2;
 }
 
 cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter) {
   if (a.nstrands <= 0 || a.nverts <= 0) return cudaSuccess;
+  if (a.prefer_latency && wave_kernel_eligible(a)) return launch_step_wave(a, math, stream);
   if (tile_counter && stream_kernel_eligible(a)) {
     if (a.nverts != 4 || a.nstrands % 2 == 0) return launch_step_stream(a, math, stream, tile_counter);
     // nverts == 4 pairs strands into 128-byte tensor rows: the last strand of an odd count takes the per-strand kernel

@@ -33,6 +33,7 @@ struct StepArgs {
   // than the load of the same chunk for the next pass (the tile ring prefetches two chunks ahead).
   int passes;
   int group_tiles;
+  int prefer_latency;     // bh_set_step_policy: take the latency-oriented kernel (hair_wave.cu) when the shape allows it
   Capsule caps[kMaxCapsules];
   // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
   // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.
@@ -53,7 +54,8 @@ constexpr int kSchedWords = 4;
 inline void init_sched_words(unsigned int* host_words) { host_words[0] = host_words[1] = 0u; host_words[2] = host_words[3] = 0x80000000u; }
 cudaError_t launch_step(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
 
-// Which kernel launch_step picks: 0 = streaming (hair_stream.cu), 1 = per-strand pipelined, 2 = generic.
+// Which kernel launch_step picks: 0 = streaming (hair_stream.cu), 1 = per-strand pipelined, 2 = generic, 3 = latency-oriented
+// wavefront (hair_wave.cu; only with StepArgs::prefer_latency).
 int step_kernel_kind(const StepArgs& a);
 
 // hair_stream.cu
@@ -65,5 +67,10 @@ bool stream_kernel_eligible(const StepArgs& a);
 bool stream_fusion_eligible(const StepArgs& a, int passes, bool always = true);
 cudaError_t selftest_inversesqrt(unsigned long long* mismatches);
 cudaError_t launch_step_stream(const StepArgs& a, int math, cudaStream_t stream, unsigned int* tile_counter);
+
+// hair_wave.cu: 8 lanes per strand, one constraint iteration each (8 iterations, any nverts, sphere + capsules); runs
+// StepArgs::passes consecutive steps in one launch.
+bool wave_kernel_eligible(const StepArgs& a);
+cudaError_t launch_step_wave(const StepArgs& a, int math, cudaStream_t stream);
 
 }  // namespace bh

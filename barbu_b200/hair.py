@@ -20,6 +20,7 @@ from . import _build
 
 BH_OK, BH_ERR_INVALID, BH_ERR_CUDA, BH_ERR_NOT_INITIALIZED, BH_ERR_UNSUPPORTED, BH_ERR_OVERFLOW = range(6)
 BH_MATH_EXACT, BH_MATH_FAST = 0, 1
+BH_POLICY_THROUGHPUT, BH_POLICY_LATENCY, BH_POLICY_AUTO = 0, 1, 2
 BH_SCALP_ROW_MAJOR, BH_SCALP_COLUMN_MAJOR = 0, 1
 BH_PLANE_POSITION, BH_PLANE_VELOCITY, BH_PLANE_TANGENT = 0, 1, 2
 BH_MAX_CAPSULES = 8
@@ -29,7 +30,7 @@ ABI_SYMBOLS = (
     "bh_create", "bh_destroy", "bh_set_stream", "bh_reset_stream", "bh_synchronize", "bh_default_params", "bh_set_params",
     "bh_get_params", "bh_set_bounding_sphere", "bh_upload", "bh_download", "bh_device_plane",
     "bh_random_values", "bh_init_strands", "bh_init_sphere_scalp", "bh_init_tangents_host",
-    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_group_set_substep_fusion", "bh_step_host", "bh_step_readback", "bh_host_alloc",
+    "bh_sphere_scalp_triangles", "bh_init_sphere_scalp_ordered", "bh_sphere_scalp_triangles_ordered", "bh_load_obj_scalp", "bh_free", "bh_build_patch_indices", "bh_step", "bh_set_substep_fusion", "bh_group_set_substep_fusion", "bh_set_step_policy", "bh_step_host", "bh_step_readback", "bh_host_alloc",
     "bh_host_free", "bh_tess_set_patches", "bh_tess_stream_count", "bh_tess_stream", "bh_tess_device_buffer", "bh_launch_count", "bh_step_kernel_kind", "bh_selftest_math", "bh_set_skin", "bh_skin_roots", "bh_dq_palette_from_matrices", "bh_register_gl_buffer",
     "bh_unregister_gl_buffer", "bh_register_device_buffer", "bh_unregister_device_buffer", "bh_buffer_map_stats", "bh_last_error", "bh_version",
     "bh_state_checksum", "bh_save_state", "bh_peek_state", "bh_load_state",
@@ -123,6 +124,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         "bh_unregister_device_buffer": ([vp], C.c_int),
         "bh_buffer_map_stats": ([vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)], C.c_int),
         "bh_group_set_substep_fusion": ([vp, C.c_int], C.c_int),
+        "bh_set_step_policy": ([vp, C.c_int], C.c_int),
         "bh_host_alloc": ([C.POINTER(vp), C.c_uint64], C.c_int),
         "bh_host_free": ([vp], C.c_int),
         "bh_tess_set_patches": ([vp, vp, i64], C.c_int),
@@ -311,6 +313,10 @@ class HairSim:
         p = self.get_params()
         _apply_param_keywords(p, kw)
         self.set_params(p)
+
+    def set_step_policy(self, policy: int):
+        """BH_POLICY_THROUGHPUT (default), BH_POLICY_LATENCY (wavefront kernel: small scalps), BH_POLICY_AUTO (by size)."""
+        _check(self._lib.bh_set_step_policy(self._h, policy))
 
     def set_substep_fusion(self, enabled, always: bool = False):
         """step(dt, k > 1) as k passes of ONE launch (tiles re-read from L2 between substeps); bit-identical results.
@@ -796,6 +802,7 @@ class Hair:
         N = self.params.ncontrol_points
         S = scalp.nvertices                                                 # hair.cc:58
         self.sim = HairSim(S, N, self.device)
+        self.sim.set_step_policy(BH_POLICY_AUTO)                            # small scalps (the reference's own: 448 x 4): latency kernel
         # init_simulation (hair.cc:236-361): device expansion + host tangents
         rv = random_values(self.params.seed, 0, S)
         self.sim.init_strands(scalp.positions, scalp.normals, rv, self.params.maxlength)

@@ -129,6 +129,16 @@ int  bh_build_patch_indices(const int32_t* tri_indices, int64_t nfaces, int nver
 /* ---- Hair::update(dt) (hair.cc:89-125) ------------------------------------------------------- */
 /* `substeps` launches of the fused step kernel, each with dt/substeps (substeps = 1: reference). */
 int  bh_step(bh_sim* sim, float dt, int substeps);
+/* Which step kernel serves bh_step. BH_POLICY_THROUGHPUT (default): the streaming kernel — fewest instructions and HBM bytes
+ * per vertex, but a launch never takes less than 10-14 us (one warp's pipeline latency). BH_POLICY_LATENCY: the wavefront
+ * kernel — eight lanes per strand, one constraint iteration each; about twice the instructions, a quarter of the latency;
+ * the substeps of a bh_step run as passes of its one launch. BH_POLICY_AUTO: LATENCY up to 2^18 vertices (the reference's
+ * own scalp is 448 x 4), THROUGHPUT above. Same arithmetic, bit-identical results (8 iterations; other counts keep the
+ * generic kernel). The Hair adaptors (barbu_hair.hpp, barbu_b200.Hair) set AUTO. */
+#define BH_POLICY_THROUGHPUT 0
+#define BH_POLICY_LATENCY    1
+#define BH_POLICY_AUTO       2
+int  bh_set_step_policy(bh_sim* sim, int policy);
 /* Frame-level substep fusion (off by default = one launch per substep, the reference's one dispatch per step). When on,
  * bh_step(dt, substeps > 1) runs the substeps of the frame as consecutive PASSES of one launch of the streaming kernel: a warp
  * takes a group of tiles through all passes before it asks for more, so a pass re-reads from L2 what the previous one
@@ -152,7 +162,8 @@ int  bh_host_free(void* ptr);
 /* Kernel launches issued by this sim so far (bench.py's gpu_launches claim). */
 int64_t bh_launch_count(const bh_sim* sim);
 /* Which step kernel the current shape/parameters select: 0 streaming (TMA tiles + packed fp32x2; any nverts >= 2,
- * 8 iterations, sphere + capsules), 1 per-strand pipelined (nverts = 1, corner cases), 2 generic (any iteration count). */
+ * 8 iterations, sphere + capsules), 1 per-strand pipelined (nverts = 1, corner cases), 2 generic (any iteration count),
+ * 3 latency-oriented wavefront (bh_set_step_policy). */
 int  bh_step_kernel_kind(const bh_sim* sim);
 /* Exhaustive device check of the exact profile's branch-free 1/sqrt(x) (scalar and packed fp32x2 forms) against
  * the IEEE-754 builtins over every finite binary32 >= 2^-102. *mismatches must come back 0. */

@@ -84,6 +84,7 @@ class Hair {
     if (params_.b200.devices.size() > 1) { setup_group(scalp, S, N); return; }
     if (params_.b200.devices.size() == 1) params_.b200.device = params_.b200.devices[0];
     if (!check(bh_create(&sim_, S, N, params_.b200.device), "bh_create")) { sim_ = nullptr; return; }
+    bh_set_step_policy(sim_, BH_POLICY_AUTO);      // small scalps (the reference's own: 448 x 4) take the latency-oriented kernel
     // init_simulation (hair.cc:236-361): jitter on the host exactly as the reference, expansion on the device,
     // tangent plane on the host (libm + simplex noise), uploaded to plane 2.
     std::vector<float> rv(static_cast<size_t>(S));

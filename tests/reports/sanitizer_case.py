@@ -79,3 +79,15 @@ with bb.HairSim(S, N) as a, bb.HairSim(S, N) as b:
     b.set_skin(root, np.tile(np.arange(4, dtype=np.int32), (S, 1)), np.full((S, 3), 0.25, np.float32)); b.skin_roots(dq); b.step(float(DT), 1)
     print("ok readback / device buffer / skin", b.buffer_map_stats(), flush=True)
 out.free()
+# ---- the latency-oriented wavefront kernel (bh_set_step_policy): ragged strand counts, capsules, passes
+for (S, N, k) in [(449, 4, 4), (130, 16, 1), (37, 32, 2), (5, 1, 1)]:
+    pos, vel = ragged_state(S, N)
+    par = po.default_params(dt=float(np.float32(DT) / np.float32(k)), scale=1.45, sphere=SPHERE)
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(2 * k): po.step(rp, rv, S, N, par)
+    with bb.HairSim(S, N) as sim:
+        sim.configure(scale=1.45, sphere=SPHERE); sim.set_step_policy(bb.BH_POLICY_LATENCY); sim.upload(pos, vel)
+        for _ in range(2): sim.step(float(DT), k)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp); assert_bit_equal(gv, rv)
+    print("ok wave", S, N, k, flush=True)

@@ -136,7 +136,8 @@ def test_reference_head_scalp_asset_matches_golden():
 
 
 @pytest.mark.gpu
-def test_hair_setup_from_obj_reference_default_shape_bit_exact(tmp_path):
+@pytest.mark.parametrize("policy", ["adaptor default", "throughput"])
+def test_hair_setup_from_obj_reference_default_shape_bit_exact(tmp_path, policy):
     """Hair::setup(resource) + 10 updates with the reference's defaults (N = 4 control points, uScaleFactor 1.45),
     on an OBJ scalp written here (a bumpy quad patch), against the oracle."""
     n = 12
@@ -163,7 +164,11 @@ def test_hair_setup_from_obj_reference_default_shape_bit_exact(tmp_path):
     h.set_bounding_sphere(sphere)
     h.setup(path)
     assert h.initialized() and h.nroots == S == n * n
-    assert h.sim.kernel_kind == 0                      # N = 4: the streaming kernel, two strands per 128-byte tensor row
+    if policy == "throughput":
+        h.sim.set_step_policy(bb.BH_POLICY_THROUGHPUT)
+        assert h.sim.kernel_kind == 0                  # N = 4: the streaming kernel, two strands per 128-byte tensor row
+    else:
+        assert h.sim.kernel_kind == 3                  # the adaptor asks for BH_POLICY_AUTO: a scalp this small takes the latency kernel
     for _ in range(10):
         h.update(float(DT))
     gp, gv, gt = h.sim.download(tan=True)
