@@ -18,7 +18,7 @@ cp(f"launches_{tag}.csv", f"{rnd}_ncu_launches.csv")
 cp("probe_box.txt", f"{rnd}_probe_box.txt")
 cp(f"smi_{tag}.txt", f"{rnd}_smi.txt")
 for f in ("ubench_f32x2.txt", "ubench_lat.txt", "isqrt_probe.txt", "occ_sweep.txt", "launch_probe_exact.txt", "launch_probe_fast.txt",
-          "drift_report.txt", "sweep_v28.txt", "bench_2gpu.json"):
+          "sweep_v28.txt"):   # drift_report.txt and bench_2gpu.json are copied by hand when a run produced them
     cp(f, f"{rnd}_{f}")
 
 # ---- launch list: share of the step kernel in the bench command -------------------------------------------------
