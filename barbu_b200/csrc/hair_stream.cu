@@ -145,6 +145,17 @@ struct PackedExact {
   static __device__ __forceinline__ V3p push_out(V3p c, V3p pt, u64 ninv, u64 r, u64 nz) {
     return { sub2(c.x, mul(r, mul(pt.x, ninv, nz), nz)), sub2(c.y, mul(r, mul(pt.y, ninv, nz), nz)), sub2(c.z, mul(r, mul(pt.z, ninv, nz), nz)) };
   }
+  // The same for a sphere centred on (+0, +0, +0): 0 + RN(r * n) as ONE fused operation, RN(r * n + (+0)). For a product
+  // that does not round to zero the two agree trivially (adding zero does not move a rounding), and an exactly zero product
+  // gives +0 both ways. They would differ — by the sign of a zero — only for a non-zero product that UNDERFLOWS to zero,
+  // and a vertex that is pushed out cannot produce one: it lies inside the sphere, so r / |pt| > 1 - 2^-21 and
+  // |r * n.x| >= |pt.x| (1 - 2^-21) up to one rounding of n.x, which keeps every non-zero coordinate (the smallest
+  // subnormal included: RN(k d / |pt|) >= 1 d whenever r * that can matter) away from the underflow threshold; the lanes that
+  // are NOT pushed out discard this value. Saves the three packed additions per stage pair.
+  static __device__ __forceinline__ V3p push_out_origin(V3p pt, u64 ninv, u64 r, u64 nz) {
+    const u64 pz = 0ull;                                                      // (+0.0f, +0.0f)
+    return { fma2(r, neg2(mul(pt.x, ninv, nz)), pz), fma2(r, neg2(mul(pt.y, ninv, nz)), pz), fma2(r, neg2(mul(pt.z, ninv, nz)), pz) };
+  }
 };
 
 struct PackedFast {
@@ -164,6 +175,7 @@ struct PackedFast {
     const u64 s = mul2_contractable(r, isq);
     return { fma2(pt.x, s, c.x), fma2(pt.y, s, c.y), fma2(pt.z, s, c.z) };
   }
+  static __device__ __forceinline__ V3p push_out_origin(V3p pt, u64 isq, u64 r, u64 nz) { return push_out(V3p{ 0ull, 0ull, 0ull }, pt, isq, r, nz); }
 };
 
 __device__ __forceinline__ V3p sub3(V3p a, V3p b) { return { sub2(a.x, b.x), sub2(a.y, b.y), sub2(a.z, b.z) }; }
@@ -447,7 +459,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     const u64 r2p = pk(a.r, a.r);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const V3p Q = PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
+      const V3p Q = ORIGIN ? PM::push_out_origin(pt[q], ninvc[q], r2p, nz) : PM::push_out(c2, pt[q], ninvc[q], r2p, nz);
       C[q] = pk3(sel3_lt(lo(dpc[q]), a.r2, lo3(Q), lo3(D[q])), sel3_lt(hi(dpc[q]), a.r2, hi3(Q), hi3(D[q])));
     }
     // stage 7 is done: keep its final position and the collision normal for the step that writes it out
