@@ -109,3 +109,29 @@ def test_wave_kernel_fast_profile_close_to_exact():
     ok = np.isfinite(a).all(axis=1) & np.isfinite(b).all(axis=1)
     rel = np.abs(a[ok] - b[ok]).max(axis=1) / np.maximum(np.abs(a[ok]).max(axis=1), 1e-3)
     assert np.median(rel) < 1e-6 and np.quantile(rel, 0.99) < 1e-5            # a rough state with contacts: the bulk, not the worst vertex
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_wave_kernel_behind_the_host_buffer_entry_points(fuse):
+    """bh_step_host and bh_step_readback slice the shard and launch per slice: under the latency policy (decided by the
+    sim's size, not the slice's) they run the wavefront kernel too and still equal step + download bit for bit."""
+    S, N, k = 9001, 16, 3
+    pos, vel = ragged_state(S, N)
+    with bb.HairSim(S, N) as a, bb.HairSim(S, N) as b:
+        for sim in (a, b):
+            sim.configure(scale=1.45, sphere=SPHERE); sim.set_step_policy(bb.BH_POLICY_AUTO); sim.set_substep_fusion(fuse, always=True)
+            assert sim.kernel_kind == 3
+            sim.upload(pos, vel)
+        out = bb.PinnedBuffer(4 * S * N)
+        hp, hv = pos.reshape(-1).copy(), vel.reshape(-1).copy()
+        for _ in range(3):
+            a.step(float(DT), k)
+            b.step_readback(float(DT), k, out.array)
+        wp, wv, _ = a.download()
+        assert_bit_equal(out.array.reshape(-1, 4), wp, "read-back positions")
+        assert_bit_equal(b.download()[1], wv, "velocities left on the device")
+        for _ in range(3):
+            b.step_host(float(DT), k, hp, hv)
+        b.upload(pos, vel)
+        assert_bit_equal(hp.reshape(-1, 4), wp, "bh_step_host"); assert_bit_equal(hv.reshape(-1, 4), wv)
+        out.free()
