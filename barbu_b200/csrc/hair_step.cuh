@@ -44,6 +44,7 @@ struct StepArgs {
   // ... and in front of both, the shell around the sphere's centre that holds all capsules (squared radii, with margins):
   // the step already has every vertex's squared distance to that centre.
   float cap_lo2, cap_hi2;
+  float r2_maybe;         // streaming kernel, exact profile: r^2 (1 + 2^-20) — above it a contracted |p - c|^2 rules a push-out out
 };
 
 // Launch one fused step (integrate -> K x (FTL, collide) -> velocity fix) in place.

@@ -121,6 +121,7 @@ struct V3p { u64 x, y, z; };                     // lo half: stage a, hi half: s
 struct PackedExact {
   typedef MathExact S;
   static constexpr bool kRangeChecked = true;
+  static constexpr bool kTwoStageTest = true;      // stream_step phase T: a contracted sum of squares decides "nobody is near the sphere"
   static __device__ __forceinline__ u64 mul(u64 a, u64 b, u64 nz) { return fma2(a, b, nz); }   // RN(a*b + -0) == RN(a*b), sign of zero included
   static __device__ __forceinline__ u64 dot(V3p a, V3p b, u64 nz) { return add2(add2(mul(a.x, b.x, nz), mul(a.y, b.y, nz)), mul(a.z, b.z, nz)); }
   // -(1 / sqrt(x)) for both halves, finite x >= 2^-102: the sequence of MathExact::inversesqrt_in_range, with the
@@ -161,6 +162,7 @@ struct PackedExact {
 struct PackedFast {
   typedef MathFast S;
   static constexpr bool kRangeChecked = false;
+  static constexpr bool kTwoStageTest = false;     // its dot IS the contracted sum
   static __device__ __forceinline__ u64 mul(u64 a, u64 b, u64) { return mul2_contractable(a, b); }
   static __device__ __forceinline__ u64 dot(V3p a, V3p b, u64) { return fma2(a.z, b.z, fma2(a.y, b.y, mul2_contractable(a.x, b.x))); }
   // this profile keeps the inverse square root with its own sign (one MUFU.RSQ per half)
@@ -419,10 +421,33 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   V3p pt[4];
   u64 dpc[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
-    dpc[q] = PM::dot(pt[q], pt[q], nz);
+  for (int q = 0; q < 4; ++q) pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
+  if (PM::kTwoStageTest && !SEP && !CAPS) {
+    // The exact squared distance (five packed operations per pair, the reference's rounding sequence) is only NEEDED by a
+    // vertex that is pushed out; whether any vertex is, a contracted sum of squares (three operations) decides for all
+    // but the warps within 2^-20 relative of the surface: both sums carry at most three roundings of at most the true value,
+    // so fma-chain >= r^2 (1 + 2^-20) implies exact >= r^2 (StepArgs::r2_maybe, +inf where that argument does not hold:
+    // subnormal radii). A step that follows a push-out (SEP) nearly always pushes out again and goes straight to the
+    // exact sum; so does the capsule variant, whose shell test wants the exact distances anyway.
+    u64 df[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) df[q] = fma2(pt[q].z, pt[q].z, fma2(pt[q].y, pt[q].y, mul2_contractable(pt[q].x, pt[q].x)));
+    const float inf = __int_as_float(0x7f800000);
+    if (RS == 8) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j == q) df[q] = pk(inf, hi(df[q]));
+        if (j == q + 4) df[q] = pk(lo(df[q]), inf);
+      }
+    } else if (RS == 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (root_in_stage<RS>(j, q)) df[q] = pk(inf, inf);
+    }
+    if (!__any_sync(0xffffffffu, min8(df) < a.r2_maybe)) return false;
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dpc[q] = PM::dot(pt[q], pt[q], nz);
   // roots do not collide (cs:149-151: index > 0): their distance becomes +inf, which no radius exceeds; in the capsule variant
   // NaN, which the minimum AND the maximum below skip (fminf / fmaxf return the other operand) and which compares false too
   const float no_hit = __int_as_float(CAPS ? 0x7fffffff : 0x7f800000);
@@ -799,6 +824,12 @@ template <class PM, bool ORIGIN, int NS, bool CAPS, bool FUSED>
 cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned int* tile_counter, int variant) {
   StepArgs a = a_in;
   a.tip_step = a.nverts % kK == 0 ? kK - 1 : a.nverts % kK - 1;
+  {
+    // threshold of the two-stage sphere test: r^2 (1 + 2^-20), rounded up; the error argument needs normal numbers
+    const double t = (double)a.r2 * (1.0 + 9.5367431640625e-07);
+    a.r2_maybe = (a.r2 >= 7.888609052210118e-31f && t < 3.0e38) ? std::nextafter((float)t, INFINITY) : INFINITY;   // r^2 >= 2^-100
+    if (!(a.r2_maybe >= a.r2)) a.r2_maybe = INFINITY;                          // NaN radius: never skip the exact test
+  }
   if (CAPS) fill_capsule_bounds(a);
   static DeviceInfo info[64];
   static std::mutex mu;
