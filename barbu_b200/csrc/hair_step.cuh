@@ -40,10 +40,14 @@ struct StepArgs {
   float capb[kMaxCapsules][4];
   // ... and a capsule-shaped second bound for the warps the first one lets through: axis (b - a), 1 / |b - a|^2 (0 for a
   // degenerate capsule) and the squared radius with its margin, for a packed fast-arithmetic distance to the axis.
-  float capt[kMaxCapsules][8];   // abx, aby, abz, inv_l2, r2_tight, 0, 0, 0
+  float capt[kMaxCapsules][8];   // abx, aby, abz, inv_l2, r2_tight, r_tight (rounded up), 0, 0
   // ... and in front of both, the shell around the sphere's centre that holds all capsules (squared radii, with margins):
   // the step already has every vertex's squared distance to that centre.
   float cap_lo2, cap_hi2;
+  // ... and the error terms of the temporal bound (stream_step, capsule variant): per step a lane's lower bound on its distance
+  // to the capsules shrinks by its largest rest length plus cap_e0 + cap_e1 * max |p - c|^2 (rounding of the positions and of
+  // the distance evaluation, generously)
+  float cap_e0, cap_e1;
   float r2_maybe;         // streaming kernel, exact profile: r^2 (1 + 2^-20) — above it a contracted |p - c|^2 rules a push-out out
 };
 

@@ -118,7 +118,16 @@ constexpr u64 kHalf2 = 0x3f0000003f000000ull;
 
 #ifdef BH_STATS   // debug build only (tools/stats_build.sh): contact statistics of the step loop, printed by the last warp of a launch
 __device__ unsigned long long g_stats[16];
-#define BH_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+__device__ __forceinline__ unsigned long long* bh_warp_stats() {           // per-warp counters in shared memory, flushed once per launch
+  __shared__ unsigned long long w[8][16];
+  return w[threadIdx.x >> 5];
+}
+#define BH_STAT(i, v) (bh_warp_stats()[i] += (unsigned long long)(v))
+#define BH_T0(name) const long long name = clock64()
+#define BH_T1(i, name) do { if ((threadIdx.x & 31) == 0) BH_STAT(i, clock64() - name); } while (0)
+#else
+#define BH_T0(name)
+#define BH_T1(i, name)
 #endif
 
 struct V3p { u64 x, y, z; };                     // lo half: stage a, hi half: stage a + 4
@@ -227,6 +236,9 @@ struct Pipe {
   V3 heldC, heldN;
   bool heldHit;
   bool heldCap;    // capsule variant, warp-uniform: that vertex went through the capsule chain -> recompute it with its velocity
+  // capsule variant, temporal bound (per lane): every position this lane has in flight is at least `slack` away from every
+  // capsule's widened surface; <= 0 (or NaN): nothing is known. `lmax`: largest |sf * rest| this lane has seen.
+  float slack, lmax;
 };
 
 struct Quad { u64 v[4]; };
@@ -239,14 +251,16 @@ template <class PM> __device__ __noinline__ Quad neg_inversesqrt_slow(Quad x) {
 // ninv[a] = -inversesqrt(x[a]). The branch-free sequence is issued unconditionally; when some lane of the warp has an
 // operand outside its range (`ok` false: rare), the whole warp recomputes with the IEEE builtins.
 template <class PM>
-__device__ __forceinline__ void neg_inversesqrt_batch(const u64 (&x)[4], u64 (&ninv)[4], bool ok, u64 nz) {
+__device__ __forceinline__ bool neg_inversesqrt_batch(const u64 (&x)[4], u64 (&ninv)[4], bool ok, u64 nz) {
 #pragma unroll
   for (int a = 0; a < 4; ++a) ninv[a] = PM::neg_inversesqrt_in_range(x[a], nz);
   if (PM::kRangeChecked && !__all_sync(0xffffffffu, ok)) {
     const Quad r = neg_inversesqrt_slow<PM>(Quad{ { x[0], x[1], x[2], x[3] } });
 #pragma unroll
     for (int a = 0; a < 4; ++a) ninv[a] = r.v[a];
+    return true;
   }
+  return false;                                                               // warp-uniform: whether the IEEE path ran
 }
 
 __device__ __forceinline__ float min8(const u64 (&v)[4]) {
@@ -293,28 +307,16 @@ template <class M> __device__ __noinline__ PosVel all_pos_vel_slow(const StepArg
   return { p, w };
 }
 
-// Conservative capsule test of eight positions: true when some position lies inside a capsule's bounding sphere.
-__device__ __forceinline__ bool caps_may_touch(const StepArgs& a, const V3p (&X)[4]) {
-  bool touch = false;
-#pragma unroll 1
-  for (int k = 0; k < a.ncaps; ++k) {
-    const V3p m = { pk(a.capb[k][0], a.capb[k][0]), pk(a.capb[k][1], a.capb[k][1]), pk(a.capb[k][2], a.capb[k][2]) };
-    u64 dd[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const V3p e = sub3(X[q], m);
-      dd[q] = fma2(e.z, e.z, fma2(e.y, e.y, mul2_contractable(e.x, e.x)));  // a bound, not a result: contraction is fine
-    }
-    touch = touch || (min8(dd) < a.capb[k][3]);
-  }
-  return touch;
-}
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// Second, capsule-shaped bound for a warp the bounding spheres let through: squared distance to the capsule's axis in fast
-// packed arithmetic against the radius with a margin (fill_capsule_bounds). Still conservative — it only decides whether
-// the exact chain is entered — but it fits the capsule, not a sphere around it.
-__device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&X)[4]) {
+// Capsule-shaped conservative test of eight positions: squared distance to each capsule's axis in fast packed arithmetic
+// against the radius with a margin (fill_capsule_bounds). It only decides whether the exact chain is entered. Returns whether
+// this lane may touch a capsule, and in `slack` a lower bound on the distance of its eight positions to the widened surfaces
+// (before the error term the caller subtracts): the smallest sqrt(d^2) (1 - 2^-10) - r_tight. A NaN position takes no part in
+// either (fminf skips it: it cannot collide, and stays NaN until the next root resets the bound).
+__device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&X)[4], float& slack) {
   bool touch = false;
+  float sl = __int_as_float(0x7f800000);
 #pragma unroll 1
   for (int k = 0; k < a.ncaps; ++k) {
     const Capsule& c = a.caps[k];
@@ -330,8 +332,11 @@ __device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&
       const V3p e = { fma2(nt, AB.x, ap.x), fma2(nt, AB.y, ap.y), fma2(nt, AB.z, ap.z) };
       dd[q] = fma2(e.z, e.z, fma2(e.y, e.y, mul2_contractable(e.x, e.x)));
     }
-    touch = touch || (min8(dd) < a.capt[k][4]);
+    const float m = min8(dd);
+    touch = touch || (m < a.capt[k][4]);
+    sl = fminf(sl, __fmaf_rn(sqrt_approx(m), 0.9990234375f, -a.capt[k][5]));
   }
+  slack = sl;
   return touch;
 }
 
@@ -358,6 +363,11 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
             __fmaf_rn(a.dt2, a.fz, __fmaf_rn(a.dt, V.z, Pin.z)) };         // cs:181-182
     }
     lx = M::mul(a.sf, Pin.w);
+    if (CAPS) {
+      s.lmax = fmaxf(s.lmax, fabsf(lx));                                      // a NaN (out-of-bounds slot) is skipped
+      // a root starts a new chain of positions: nothing is known about it until the next test
+      if (root_in_stage<RS>(j, 0)) s.slack = __int_as_float(0xff800000);
+    }
   }
   // ---- the vertex finalised by this step (t-8): position known since the previous step ------------
   const V3 fin = hi3(s.X[3]);                                               // D(i, 8)
@@ -391,7 +401,9 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     // some, normalize(0) — must not drag its warp through the IEEE path at every step for the rest of the run.
     ok = !(min8(dp) < M::kFastLo) && !(max8(dp) >= __int_as_float(0x7f800000));
   }
-  neg_inversesqrt_batch<PM>(dp, ninv, ok, nz);
+  const bool ieeeA = neg_inversesqrt_batch<PM>(dp, ninv, ok, nz);
+  // outside the branch-free range (a segment shorter than 2^-51 or overflowing) the computed direction need not have unit length
+  if (CAPS && ieeeA) s.slack = __int_as_float(0xff800000);
 #pragma unroll
   for (int q = 3; q >= 0; --q) {
     D[q] = PM::project(s.X[q], vd[q], ninv[q], s.L[q], nz);
@@ -411,7 +423,9 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
       s.heldd = dF;
       if (SEP && !recompute && s.heldHit) fw = M::reflect(fw, s.heldN);     // cs:137, with the normal found one step ago
       if (recompute) {                                                      // sphere + capsules again from D(i, 8), now with the velocity
+        BH_T0(t4);
         const PosVel pv = all_pos_vel_slow<M>(a, fp, fw); fp = pv.p; fw = pv.w;
+        BH_T1(12, t4);
       }
       const float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out);
       float4 oV = make_float4(fw.x, fw.y, fw.z, 0.f);
@@ -483,10 +497,12 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #ifdef BH_STATS
   {
     int pairs = 0, stages = 0, lanes = 0;
+#if BH_STATS > 1   // -DBH_STATS=2: per-pair / per-stage / per-lane hit counts as well (eight more ballots per step)
     for (int q = 0; q < 4; ++q) {
       const unsigned ml = __ballot_sync(0xffffffffu, lo(dpc[q]) < a.r2), mh = __ballot_sync(0xffffffffu, hi(dpc[q]) < a.r2);
       pairs += (ml | mh) != 0; stages += (ml != 0) + (mh != 0); lanes += __popc(ml) + __popc(mh);
     }
+#endif
     if ((threadIdx.x & 31) == 0) { BH_STAT(0, 1); BH_STAT(1, any_hit); BH_STAT(2, pairs); BH_STAT(3, stages); BH_STAT(4, lanes); BH_STAT(5, SEP); }
   }
 #endif
@@ -518,31 +534,54 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   // ---- capsule extension: bound tests on the positions as the sphere left them, exact chain out of line ------------
   // Level 0, nearly free: the squared distances to the sphere centre are there already. All capsules lie inside the shell
   // cap_lo2 < |p - c|^2 < cap_hi2 (fill_capsule_bounds, with margins). The push-out above only moves a vertex outwards, onto
-  // the sphere, and cap_lo2 is either beyond the sphere's surface or zero: a warp whose eight positions all stayed below
+  // the sphere, and cap_lo2 is either beyond the sphere's surface or zero: a lane whose eight positions all stayed below
   // cap_lo2 or above cap_hi2 BEFORE the push-out has none inside the shell after it.
-  bool any_cap = __any_sync(0xffffffffu, mnc < a.cap_hi2 && max8(dpc) > a.cap_lo2);
+  // Level 1, temporal: the position a stage tests at this step lies within one rest length of the one it tested a step ago —
+  // D(i, k) = D(i-1, k) + L_i n with |n| = 1, the same iteration of the previous vertex (a root passes through the stages
+  // unchanged, so it is "within" the position it had one stage earlier) — plus, around a sphere push-out, the depth pushed
+  // out (tested positions are the pushed-out ones, the chain runs on the projected ones). A lane therefore keeps a lower
+  // bound on its distance to the capsules from its last test and lowers it every step by its largest rest length, twice the
+  // largest push-out depth of the step and the rounding terms cap_e0 + cap_e1 max |p - c|^2; while the bound stays positive
+  // no test is needed. Nothing here looks at other lanes, and a lane without knowledge (a new root, a direction from the
+  // IEEE path, NaN anywhere) has a bound that is not positive.
+  const float mxc = max8(dpc);
+  float eb = __fmaf_rn(mxc, a.cap_e1, a.cap_e0);                              // NaN when all eight positions are roots / NaN: forces a test
+  if (any_hit) eb = __fmaf_rn(fmaxf(0.f, a.r - sqrt_approx(mnc) * 0.9990234375f), 2.0f, eb);   // + 2 x (r - smallest |p - c|)
+  s.slack -= __fmaf_rn(s.lmax, 1.0009765625f, eb);
+  bool any_cap = __any_sync(0xffffffffu, mnc < a.cap_hi2 && mxc > a.cap_lo2 && !(s.slack > 0.f));
+#if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 1   // timing experiments only (results are wrong): drop everything behind level 0 / 1 / 2
+  any_cap = false;
+#endif
 #ifdef BH_STATS
   if ((threadIdx.x & 31) == 0) BH_STAT(6, any_cap);
 #endif
-  // level 1: a bounding sphere per capsule. Written out for both kinds of step so that the common one — the sphere touched
-  // nobody, and no bounding sphere either — reads the positions where they are (D) and leaves without having copied them.
+  // written out for both kinds of step so that the common one — the sphere touched nobody and no lane asks for a test — reads
+  // the positions where they are (D) and leaves without having copied them
   if (!any_hit) {
     s.heldHit = false;
-    if (any_cap) any_cap = __any_sync(0xffffffffu, caps_may_touch(a, D));
-#ifdef BH_STATS
-    if ((threadIdx.x & 31) == 0) BH_STAT(7, any_cap);
+#ifdef BH_STATS   // a skipped test that would have let a lane through (must stay zero)
+    if (!any_cap) { float d_; if (__any_sync(0xffffffffu, caps_tight_touch(a, D, d_)) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
 #endif
     if (!any_cap) { s.heldCap = false; return false; }
 #pragma unroll
     for (int q = 0; q < 4; ++q) C[q] = D[q];
   } else {
     sphere_push_out();                                                        // sets every C[q]
-    if (any_cap) any_cap = __any_sync(0xffffffffu, caps_may_touch(a, C));
 #ifdef BH_STATS
-    if ((threadIdx.x & 31) == 0) BH_STAT(7, any_cap);
+    if (!any_cap) { float d_; if (__any_sync(0xffffffffu, caps_tight_touch(a, C, d_)) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
 #endif
   }
-  if (any_cap) any_cap = __any_sync(0xffffffffu, caps_tight_touch(a, C));     // level 2: distance to the axis, fast arithmetic
+  if (any_cap) {                                                              // level 2: distance to the axes, fast arithmetic; renews the bound
+    BH_T0(t2);
+    float sl;
+    const bool touch = caps_tight_touch(a, C, sl);
+    s.slack = sl - eb;
+    any_cap = __any_sync(0xffffffffu, touch);
+    BH_T1(10, t2);
+  }
+#if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 3
+  any_cap = false;
+#endif
 #ifdef BH_STATS
   if ((threadIdx.x & 31) == 0) BH_STAT(8, any_cap);
 #endif
@@ -552,7 +591,9 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     unsigned skip = 0x80u;
 #pragma unroll
     for (int k = 0; k < 7; ++k) skip |= root_in_stage<RS>(j, k) ? (1u << k) : 0u;
+    BH_T0(t3);
     const Pos8 r = caps_slow<M>(a, Pos8{ { C[0], C[1], C[2], C[3] } }, skip);
+    BH_T1(11, t3);
 #pragma unroll
     for (int q = 0; q < 4; ++q) C[q] = r.c[q];
   }
@@ -667,8 +708,8 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) {
         tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence();
 #ifdef BH_STATS
-        printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: shell %llu spheres %llu tight %llu\n", g_stats[0], g_stats[1], g_stats[2],
-               g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[7], g_stats[8]);
+        printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: tested %llu (unused %llu) touched %llu | cycles: (unused %llu) test %llu slow %llu recompute %llu warp-total %llu | skipped tests that would have passed %llu\n", g_stats[0], g_stats[1], g_stats[2],
+               g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[7], g_stats[8], g_stats[9], g_stats[10], g_stats[11], g_stats[12], g_stats[13], g_stats[14]);
         for (int i = 0; i < 16; ++i) g_stats[i] = 0;
 #endif
       }
@@ -708,6 +749,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     }
     s.heldd = s.rootV[0] = s.rootV[1] = s.heldC = s.heldN = { 0.f, 0.f, 0.f };
     s.heldHit = s.heldCap = false;
+    s.slack = __int_as_float(0xff800000); s.lmax = 0.f;
   }
   for (int j = 0; j < kK; ++j) ring[j * 32 + lane] = 0.f;
 
@@ -715,6 +757,10 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   float* myR = ring + lane;
   bool prev_root_chunk = false, sep = false;
   unsigned int q = 0;
+#ifdef BH_STATS
+  if (lane == 0) for (int i = 0; i < 16; ++i) bh_warp_stats()[i] = 0;
+#endif
+  BH_T0(t_warp);
   for (;; ++q) {
     const int b = q & 1;
     const bool live = tC >= 0;                                              // false: the drain chunk after the last tile
@@ -745,6 +791,10 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     if (tC < 0 && lane == 0) tma_wait_read0();                              // the drain chunk reuses buffer b^1
     __syncwarp();
   }
+  BH_T1(13, t_warp);
+#ifdef BH_STATS
+  if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_stats[i], bh_warp_stats()[i]);
+#endif
   leave();
 }
 
@@ -822,6 +872,7 @@ void fill_capsule_bounds(StepArgs& b) {
     if (!(lo2 == lo2) || !(hi2 == hi2) || !std::isfinite((double)b.cx + b.cy + b.cz) || !std::isfinite(b.r)) { lo2 = 0.0f; hi2 = INFINITY; }
     b.cap_lo2 = lo2; b.cap_hi2 = hi2;
   }
+  double emag = 0.0;
   for (int k = 0; k < b.ncaps && k < kMaxCapsules; ++k) {
     const Capsule& c = b.caps[k];
     const double hx = 0.5 * ((double)c.bx - c.ax), hy = 0.5 * ((double)c.by - c.ay), hz = 0.5 * ((double)c.bz - c.az);
@@ -838,10 +889,19 @@ void fill_capsule_bounds(StepArgs& b) {
     b.capt[k][0] = abx; b.capt[k][1] = aby; b.capt[k][2] = abz;
     b.capt[k][3] = l2 > 0.0f ? 1.0f / l2 : 0.0f;
     b.capt[k][4] = std::nextafter((float)(Rt * Rt), INFINITY);
+    b.capt[k][5] = std::nextafter(std::sqrt(b.capt[k][4]), INFINITY);         // >= sqrt(r2_tight): the surface the temporal bound measures from
     if (!std::isfinite(b.capt[k][4]) || !std::isfinite(b.capt[k][3]) || !std::isfinite(l2)) {   // NaN / overflowing capsule: no second bound
-      b.capt[k][0] = b.capt[k][1] = b.capt[k][2] = b.capt[k][3] = 0.0f; b.capt[k][4] = INFINITY;
+      b.capt[k][0] = b.capt[k][1] = b.capt[k][2] = b.capt[k][3] = 0.0f; b.capt[k][4] = b.capt[k][5] = INFINITY;
     }
+    emag += std::fabs((double)c.ax) + std::fabs((double)c.ay) + std::fabs((double)c.az) + std::fabs((double)c.bx) + std::fabs((double)c.by) + std::fabs((double)c.bz);
   }
+  // Temporal bound: |p| <= |p - c| + |c| <= (1 + |p - c|^2) / 2 + |c|, and every rounding involved (a position coordinate per
+  // step; p - a, the closest point on the axis and the distance to it at a test) is below 2^-20 of |p| + |a| + |b|.
+  // 2^-17 of (1 + |p - c|^2 + |c| + |a| + |b|) covers them eight times over.
+  emag += 1.0 + std::fabs((double)b.cx) + std::fabs((double)b.cy) + std::fabs((double)b.cz);
+  b.cap_e1 = 7.62939453125e-06f;                                               // 2^-17
+  b.cap_e0 = std::nextafter((float)(emag * 7.62939453125e-06), INFINITY);
+  if (!std::isfinite(b.cap_e0)) b.cap_e0 = INFINITY;                            // never skip a test
 }
 
 // Tiles per group of a fused launch: the smallest count with group_tiles * chunks >= 4 (see StepArgs::group_tiles).
