@@ -66,14 +66,7 @@ __device__ __forceinline__ void collide_all_pos_vel(const StepArgs& a, V3& p, V3
   }
 }
 
-// ---- variants for the streaming kernel, which fills StepArgs::capb ----------------------------------------------
-// A position outside the bounding sphere of a capsule cannot satisfy that capsule's exact test (the bound carries a
-// margin far above fp32 rounding, see fill_capsule_bounds), so skipping the capsule there changes no result; a NaN
-// position compares false here and fails the exact `dp < r2` as well.
-__device__ __forceinline__ bool capsule_bound_hit(const float (&b)[4], V3 p) {
-  const float dx = p.x - b[0], dy = p.y - b[1], dz = p.z - b[2];
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < b[3];
-}
+// ---- variants for the streaming kernel, which fills StepArgs::capt ----------------------------------------------
 // The capsule-shaped bound of StepArgs::capt for one position: squared distance to the axis in fast arithmetic against the
 // widened radius — the scalar form of caps_tight_touch() in hair_stream.cu, operation for operation, so that a lane passes
 // here exactly when it made its warp pass there. Out of the warps that reach the exact chain only few LANES (and few of the
@@ -85,17 +78,6 @@ __device__ __forceinline__ bool capsule_tight_hit(const Capsule& c, const float 
   const float nt = -__saturatef(d * t[3]);                                   // -clamp(t, 0, 1); NaN -> 0
   const float ex = fmaf(nt, t[0], apx), ey = fmaf(nt, t[1], apy), ez = fmaf(nt, t[2], apz);
   return fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < t[4];
-}
-// The capsules alone, position only (the streaming kernel pushes out of the sphere in packed form first).
-template <class M>
-__device__ __forceinline__ V3 collide_caps_pos_bounded(const StepArgs& a, V3 p) {
-#pragma unroll 1
-  for (int q = 0; q < a.ncaps; ++q) {
-    if (!capsule_tight_hit(a.caps[q], a.capt[q], p)) continue;
-    const float r = a.caps[q].r;
-    p = collide_pos<M>(p, capsule_center<M>(a.caps[q], p), r, M::mul(r, r));
-  }
-  return p;
 }
 // Sphere, then capsules, position and velocity (the last iteration of a vertex).
 template <class M>

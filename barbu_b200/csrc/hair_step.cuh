@@ -35,10 +35,7 @@ struct StepArgs {
   int group_tiles;
   int prefer_latency;     // bh_set_step_policy: take the latency-oriented kernel (hair_wave.cu) when the shape allows it
   Capsule caps[kMaxCapsules];
-  // Filled by the streaming launcher: bounding sphere of each capsule (centre xyz, squared radius with a safety
-  // margin) — a conservative "may touch" test in front of the exact capsule arithmetic.
-  float capb[kMaxCapsules][4];
-  // ... and a capsule-shaped second bound for the warps the first one lets through: axis (b - a), 1 / |b - a|^2 (0 for a
+  // Filled by the streaming launcher: a capsule-shaped bound in front of the exact capsule arithmetic: axis (b - a), 1 / |b - a|^2 (0 for a
   // degenerate capsule) and the squared radius with its margin, for a packed fast-arithmetic distance to the axis.
   float capt[kMaxCapsules][8];   // abx, aby, abz, inv_l2, r2_tight, r_tight (rounded up), 0, 0
   // ... and in front of both, the shell around the sphere's centre that holds all capsules (squared radii, with margins):
@@ -48,6 +45,9 @@ struct StepArgs {
   // to the capsules shrinks by its largest rest length plus cap_e0 + cap_e1 * max |p - c|^2 (rounding of the positions and of
   // the distance evaluation, generously)
   float cap_e0, cap_e1;
+  // ... and the per-capsule constants of the exact chain as capsule_center() / collide_pos() compute them (single IEEE
+  // operations in their order: the host's float arithmetic gives the same bits): b - a, |b - a|^2, r * r
+  float capx[kMaxCapsules][8];   // abx, aby, abz, l2, r2, 0, 0, 0
   float r2_maybe;         // streaming kernel, exact profile: r^2 (1 + 2^-20) — above it a contracted |p - c|^2 rules a push-out out
 };
 

@@ -54,6 +54,12 @@ typedef unsigned long long u64;
 #ifndef BH_DRAG
 #define BH_DRAG 1
 #endif
+#ifndef BH_CAPS_ONE_BODY
+#define BH_CAPS_ONE_BODY 1
+#endif
+#ifndef BH_CAPS_PAIRS
+#define BH_CAPS_PAIRS 1
+#endif
 constexpr int kK = 8;                            // constraint iterations == pipeline depth == vertices per chunk
 #ifndef BH_STREAM_WARPS
 #define BH_STREAM_WARPS 4
@@ -290,16 +296,69 @@ __device__ __forceinline__ bool root_in_stage(const int j, const int stage) {
 //          chain with its final velocity one step later, so no collision normals are carried.
 // The exact capsule arithmetic runs for few warps and must not bloat the step body (the instruction cache holds the hot
 // loop only if the rare paths stay out of line): one out-of-line copy each, one call per step.
-struct Pos8 { V3p c[4]; };                       // the eight positions of a step: pair q = stages q (lo) and q + 4 (hi)
-template <class M> __device__ __noinline__ Pos8 caps_slow(const StepArgs& a, Pos8 x, const unsigned skip) {
+// The capsule chain of collide_all_pos (hair_collide.cuh) for the eight positions of a step, branch-free per lane: pair by
+// pair, for every capsule in turn the closest point on its axis (IEEE division, scalar), then the sphere push-out in the
+// packed form the step uses for the sphere itself. Operation for operation the scalar chain — a lane's arithmetic does not
+// depend on what other lanes do; the votes only skip work whose result every lane would discard. The positions travel
+// through local memory and one pair is in registers at a time: the function must fit into the registers the step leaves
+// free, or the step itself starts spilling (all eight in registers: 280 bytes of spills in the hot loop, capsules nothing
+// can reach 2.36 -> 3.2 ms). `skip`: positions that do not collide (roots; the vertex in stage 7, which the next step
+// recomputes). `cmask`: capsules whose bound some lane passed on the positions as they came in — a capsule outside it is
+// visited only once an earlier one has moved something in that pair.
+template <class PM> __device__ __noinline__ void caps_packed(const StepArgs& a, V3p* x, const unsigned skip, const unsigned cmask, const u64 nz) {
+  typedef typename PM::S M;
+  constexpr int W = BH_CAPS_PAIRS;                                            // pairs in registers at a time (independent chains)
+  const float inf = __int_as_float(0x7f800000);
 #pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
-    V3 l = lo3(x.c[q]), h = hi3(x.c[q]);
-    if (!((skip >> q) & 1u)) l = collide_caps_pos_bounded<M>(a, l);
-    if (!((skip >> (q + 4)) & 1u)) h = collide_caps_pos_bounded<M>(a, h);
-    x.c[q] = pk3(l, h);
+  for (int q0 = 0; q0 < 4; q0 += W) {
+    V3p p[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) p[i] = x[q0 + i];
+    bool moved = false;
+#pragma unroll 1
+    for (int k = 0; k < a.ncaps; ++k) {
+      if (!moved && !((cmask >> k) & 1u)) continue;
+      const Capsule& c = a.caps[k];
+      const V3 ab = { a.capx[k][0], a.capx[k][1], a.capx[k][2] };               // b - a, |b - a|^2 and r * r as the scalar chain forms them
+      const float l2 = a.capx[k][3];
+      const float r = c.r, r2 = a.capx[k][4];
+      const V3p A2 = { pk(c.ax, c.ax), pk(c.ay, c.ay), pk(c.az, c.az) };
+      V3p ctr[W], pt[W];
+      u64 dp[W];
+      float mn = inf;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        ctr[i] = A2;
+        if (l2 > 0.0f) {                                                      // capsule_center(); warp-uniform
+          const V3p AB2 = { pk(ab.x, ab.x), pk(ab.y, ab.y), pk(ab.z, ab.z) };
+          const V3p ap = sub3(p[i], A2);
+          const u64 d = PM::dot(ap, AB2, nz);
+          const float tl = fminf(fmaxf(__fdiv_rn(lo(d), l2), 0.0f), 1.0f), th = fminf(fmaxf(__fdiv_rn(hi(d), l2), 0.0f), 1.0f);
+          const u64 t2 = pk(tl, th);
+          ctr[i] = { add2(A2.x, PM::mul(t2, AB2.x, nz)), add2(A2.y, PM::mul(t2, AB2.y, nz)), add2(A2.z, PM::mul(t2, AB2.z, nz)) };
+        }
+        pt[i] = sub3(p[i], ctr[i]);                                           // collide_pos()
+        dp[i] = PM::dot(pt[i], pt[i], nz);
+        if ((skip >> (q0 + i)) & 1u) dp[i] = pk(inf, hi(dp[i]));              // +inf: below no radius
+        if ((skip >> (q0 + i + 4)) & 1u) dp[i] = pk(lo(dp[i]), inf);
+        mn = fminf(mn, fminf(lo(dp[i]), hi(dp[i])));                          // a NaN takes no part: it is not below r2 either
+      }
+      if (!__any_sync(0xffffffffu, mn < r2)) continue;
+      moved = true;
+      const bool ieee = PM::kRangeChecked && __any_sync(0xffffffffu, mn < M::kFastLo);   // a hit has dp < r2: only the lower end of the range can fail
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        u64 ninv = PM::neg_inversesqrt_in_range(dp[i], nz);
+        if (ieee) ninv = PM::neg_inversesqrt_ieee(dp[i]);
+        const V3p Q = PM::push_out(ctr[i], pt[i], ninv, pk(r, r), nz);
+        p[i] = pk3(sel3_lt(lo(dp[i]), r2, lo3(Q), lo3(p[i])), sel3_lt(hi(dp[i]), r2, hi3(Q), hi3(p[i])));
+      }
+    }
+    if (moved) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) x[q0 + i] = p[i];
+    }
   }
-  return x;
 }
 struct PosVel { V3 p, w; };
 template <class M> __device__ __noinline__ PosVel all_pos_vel_slow(const StepArgs& a, V3 p, V3 w) {
@@ -311,11 +370,12 @@ __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.appro
 
 // Capsule-shaped conservative test of eight positions: squared distance to each capsule's axis in fast packed arithmetic
 // against the radius with a margin (fill_capsule_bounds). It only decides whether the exact chain is entered. Returns whether
-// this lane may touch a capsule, and in `slack` a lower bound on the distance of its eight positions to the widened surfaces
+// some lane may touch a capsule, and in `slack` a lower bound on the distance of its eight positions to the widened surfaces
 // (before the error term the caller subtracts): the smallest sqrt(d^2) (1 - 2^-10) - r_tight. A NaN position takes no part in
 // either (fminf skips it: it cannot collide, and stays NaN until the next root resets the bound).
-__device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&X)[4], float& slack) {
-  bool touch = false;
+// Returns (warp-uniform) the set of capsules whose bound some lane passed.
+__device__ __forceinline__ unsigned caps_tight_touch(const StepArgs& a, const V3p (&X)[4], float& slack) {
+  unsigned touch = 0u;
   float sl = __int_as_float(0x7f800000);
 #pragma unroll 1
   for (int k = 0; k < a.ncaps; ++k) {
@@ -333,7 +393,7 @@ __device__ __forceinline__ bool caps_tight_touch(const StepArgs& a, const V3p (&
       dd[q] = fma2(e.z, e.z, fma2(e.y, e.y, mul2_contractable(e.x, e.x)));
     }
     const float m = min8(dd);
-    touch = touch || (m < a.capt[k][4]);
+    if (__any_sync(0xffffffffu, m < a.capt[k][4])) touch |= 1u << k;
     sl = fminf(sl, __fmaf_rn(sqrt_approx(m), 0.9990234375f, -a.capt[k][5]));
   }
   slack = sl;
@@ -450,50 +510,53 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   u64 dpc[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) pt[q] = ORIGIN ? D[q] : sub3(D[q], c2);
-  if (PM::kTwoStageTest && !SEP && !CAPS) {
+  // roots do not collide (cs:149-151: index > 0): their distance becomes +inf, which no radius exceeds; in the capsule variant
+  // NaN, which the minimum AND the maximum below skip (fminf / fmaxf return the other operand) and which compares false too
+  const float no_hit = __int_as_float(CAPS ? 0x7fffffff : 0x7f800000);
+  auto mark_roots = [&](u64 (&v)[4]) {
+    if (RS == 8) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j == q) v[q] = pk(no_hit, hi(v[q]));
+        if (j == q + 4) v[q] = pk(lo(v[q]), no_hit);
+      }
+    } else if (RS == 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (root_in_stage<RS>(j, q)) v[q] = pk(no_hit, no_hit);
+    }
+  };
+  bool maybe_hit = true;                                                      // warp-uniform
+  float mnc = 0.f, mxc = 0.f;                                                 // smallest / (capsule variant) largest |p - c|^2 of this lane
+  if (PM::kTwoStageTest && !SEP) {
     // The exact squared distance (five packed operations per pair, the reference's rounding sequence) is only NEEDED by a
     // vertex that is pushed out; whether any vertex is, a contracted sum of squares (three operations) decides for all
     // but the warps within 2^-20 relative of the surface: both sums carry at most three roundings of at most the true value,
     // so fma-chain >= r^2 (1 + 2^-20) implies exact >= r^2 (StepArgs::r2_maybe, +inf where that argument does not hold:
     // subnormal radii). A step that follows a push-out (SEP) nearly always pushes out again and goes straight to the
-    // exact sum; so does the capsule variant, whose shell test wants the exact distances anyway.
+    // exact sum. The capsule variant's shell test and error term take the contracted sums just as well (their margins are
+    // a thousand times the difference).
     u64 df[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) df[q] = fma2(pt[q].z, pt[q].z, fma2(pt[q].y, pt[q].y, mul2_contractable(pt[q].x, pt[q].x)));
-    const float inf = __int_as_float(0x7f800000);
-    if (RS == 8) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (j == q) df[q] = pk(inf, hi(df[q]));
-        if (j == q + 4) df[q] = pk(lo(df[q]), inf);
-      }
-    } else if (RS == 4) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (root_in_stage<RS>(j, q)) df[q] = pk(inf, inf);
+    mark_roots(df);
+    mnc = min8(df);
+    maybe_hit = __any_sync(0xffffffffu, mnc < a.r2_maybe);
+    if (!maybe_hit) {
+      if (!CAPS) return false;
+      mxc = max8(df);
     }
-    if (!__any_sync(0xffffffffu, min8(df) < a.r2_maybe)) return false;
   }
+  if (maybe_hit) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dpc[q] = PM::dot(pt[q], pt[q], nz);
-  // roots do not collide (cs:149-151: index > 0): their distance becomes +inf, which no radius exceeds; in the capsule variant
-  // NaN, which the minimum AND the maximum below skip (fminf / fmaxf return the other operand) and which compares false too
-  const float no_hit = __int_as_float(CAPS ? 0x7fffffff : 0x7f800000);
-  if (RS == 8) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (j == q) dpc[q] = pk(no_hit, hi(dpc[q]));
-      if (j == q + 4) dpc[q] = pk(lo(dpc[q]), no_hit);
-    }
-  } else if (RS == 4) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (root_in_stage<RS>(j, q)) dpc[q] = pk(no_hit, no_hit);
+    for (int q = 0; q < 4; ++q) dpc[q] = PM::dot(pt[q], pt[q], nz);
+    mark_roots(dpc);
+    mnc = min8(dpc);
+    if (CAPS) mxc = max8(dpc);
   }
-  const float mnc = min8(dpc);
 
   // ---- phase B: push-outs, only when some lane of the warp touches the sphere --------------------
-  const bool any_hit = __any_sync(0xffffffffu, mnc < a.r2);
+  const bool any_hit = maybe_hit && __any_sync(0xffffffffu, mnc < a.r2);
 #ifdef BH_STATS
   {
     int pairs = 0, stages = 0, lanes = 0;
@@ -544,11 +607,18 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   // largest push-out depth of the step and the rounding terms cap_e0 + cap_e1 max |p - c|^2; while the bound stays positive
   // no test is needed. Nothing here looks at other lanes, and a lane without knowledge (a new root, a direction from the
   // IEEE path, NaN anywhere) has a bound that is not positive.
-  const float mxc = max8(dpc);
-  float eb = __fmaf_rn(mxc, a.cap_e1, a.cap_e0);                              // NaN when all eight positions are roots / NaN: forces a test
-  if (any_hit) eb = __fmaf_rn(fmaxf(0.f, a.r - sqrt_approx(mnc) * 0.9990234375f), 2.0f, eb);   // + 2 x (r - smallest |p - c|)
-  s.slack -= __fmaf_rn(s.lmax, 1.0009765625f, eb);
-  bool any_cap = __any_sync(0xffffffffu, mnc < a.cap_hi2 && mxc > a.cap_lo2 && !(s.slack > 0.f));
+  // Outside the shell nothing is tracked (the common case for capsules the hair does not reach: one vote, like a step without
+  // the temporal bound); inside it, lanes that are not in the shell themselves keep counting down.
+  const bool in_shell = mnc < a.cap_hi2 && mxc > a.cap_lo2;
+  bool any_cap = __any_sync(0xffffffffu, in_shell);
+  float eb = 0.f;
+  if (!any_cap) s.slack = __int_as_float(0xff800000);
+  else {
+    eb = __fmaf_rn(mxc, a.cap_e1, a.cap_e0);                                  // NaN when all eight positions are roots / NaN: forces a test
+    if (any_hit) eb = __fmaf_rn(fmaxf(0.f, a.r - sqrt_approx(mnc) * 0.9990234375f), 2.0f, eb);   // + 2 x (r - smallest |p - c|)
+    s.slack -= __fmaf_rn(s.lmax, 1.0009765625f, eb);
+    any_cap = __any_sync(0xffffffffu, in_shell && !(s.slack > 0.f));
+  }
 #if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 1   // timing experiments only (results are wrong): drop everything behind level 0 / 1 / 2
   any_cap = false;
 #endif
@@ -560,7 +630,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   if (!any_hit) {
     s.heldHit = false;
 #ifdef BH_STATS   // a skipped test that would have let a lane through (must stay zero)
-    if (!any_cap) { float d_; if (__any_sync(0xffffffffu, caps_tight_touch(a, D, d_)) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
+    if (!any_cap) { float d_; if (caps_tight_touch(a, D, d_) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
 #endif
     if (!any_cap) { s.heldCap = false; return false; }
 #pragma unroll
@@ -568,15 +638,16 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   } else {
     sphere_push_out();                                                        // sets every C[q]
 #ifdef BH_STATS
-    if (!any_cap) { float d_; if (__any_sync(0xffffffffu, caps_tight_touch(a, C, d_)) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
+    if (!any_cap) { float d_; if (caps_tight_touch(a, C, d_) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
 #endif
   }
+  unsigned cmask = 0u;
   if (any_cap) {                                                              // level 2: distance to the axes, fast arithmetic; renews the bound
     BH_T0(t2);
     float sl;
-    const bool touch = caps_tight_touch(a, C, sl);
+    cmask = caps_tight_touch(a, C, sl);
     s.slack = sl - eb;
-    any_cap = __any_sync(0xffffffffu, touch);
+    any_cap = cmask != 0u;
     BH_T1(10, t2);
   }
 #if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 3
@@ -592,10 +663,13 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #pragma unroll
     for (int k = 0; k < 7; ++k) skip |= root_in_stage<RS>(j, k) ? (1u << k) : 0u;
     BH_T0(t3);
-    const Pos8 r = caps_slow<M>(a, Pos8{ { C[0], C[1], C[2], C[3] } }, skip);
-    BH_T1(11, t3);
+    V3p buf[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) C[q] = r.c[q];
+    for (int q = 0; q < 4; ++q) buf[q] = C[q];
+    caps_packed<PM>(a, buf, skip, cmask, nz);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) C[q] = buf[q];
+    BH_T1(11, t3);
   }
   s.heldCap = any_cap && !root_in_stage<RS>(j, 7);                          // conservative: recomputing without a hit is a no-op
   if (any_hit || any_cap) enter_through_P();
@@ -772,7 +846,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
     // capsule variant, exact profile: one step body for both kinds of chunk (its extra tests already crowd the instruction
     // cache: with two bodies the "arms" scene of tests/reports/config3.py runs at 6.7 ms per launch instead of 5.1); the
     // fast profile's bodies are small enough to keep both (far capsules 2.25 -> 1.91 ms, "arms" 4.29 -> 3.97 ms)
-    else if (CAPS && PM::kRangeChecked) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw, root_chunk ? 0 : 8);
+    else if (BH_CAPS_ONE_BODY && CAPS && PM::kRangeChecked) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw, root_chunk ? 0 : 8);
     else if (root_chunk) stream_chunk<PM, ORIGIN, 8, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     else stream_chunk<PM, ORIGIN, 0, CAPS>(a, nz, s, sep, prev_root_chunk ? 1u : 0u, bP, bV, myR, sw);
     prev_root_chunk = root_chunk;
@@ -839,9 +913,9 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
 
 struct DeviceInfo { int sms = 0; bool ready[24] = {}; int blocks_per_sm[24] = {}; };
 
-// Bounding sphere of capsule k for caps_may_touch(): centre = midpoint of the axis, radius = half axis + capsule radius,
-// widened by 1e-3 relative + 1e-6 absolute — orders of magnitude above the fp32 rounding of either the bound or the exact
-// test it guards, so "outside the bound" implies "the exact test cannot fire".
+// Bounds in front of the exact capsule arithmetic. Each is widened by 1e-3 relative plus an absolute term — orders of
+// magnitude above the fp32 rounding of either the bound or the exact test it guards, so "outside the bound" implies "the
+// exact test cannot fire".
 void fill_capsule_bounds(StepArgs& b) {
   // Level 0: the shell around the sphere's centre that contains every capsule, lo <= |p - c| <= hi for each of their points:
   // lo = min_k (distance from c to axis k - r_k), hi = max_k (farthest axis end + r_k); margins as below. lo only counts when
@@ -875,18 +949,16 @@ void fill_capsule_bounds(StepArgs& b) {
   double emag = 0.0;
   for (int k = 0; k < b.ncaps && k < kMaxCapsules; ++k) {
     const Capsule& c = b.caps[k];
-    const double hx = 0.5 * ((double)c.bx - c.ax), hy = 0.5 * ((double)c.by - c.ay), hz = 0.5 * ((double)c.bz - c.az);
-    const double R = (std::sqrt(hx * hx + hy * hy + hz * hz) + std::fabs((double)c.r)) * (1.0 + 1e-3) + 1e-6;
-    b.capb[k][0] = (float)(c.ax + hx); b.capb[k][1] = (float)(c.ay + hy); b.capb[k][2] = (float)(c.az + hz);
-    b.capb[k][3] = std::nextafter((float)(R * R), INFINITY);
-    if (!(b.capb[k][3] == b.capb[k][3])) b.capb[k][3] = INFINITY;            // NaN capsule: always take the exact path
     // capsule-shaped bound: radius widened by 1e-3 relative plus 1e-5 of the coordinate magnitudes involved
     const float abx = c.bx - c.ax, aby = c.by - c.ay, abz = c.bz - c.az;
-    const float l2 = abx * abx + aby * aby + abz * abz;
+    const float l2xx = abx * abx, l2yy = aby * aby, l2zz = abz * abz, l2xy = l2xx + l2yy;
+    const float l2 = l2xy + l2zz;                                             // MathExact::dot(ab, ab): one rounding per operation, in its order
     const double mag = 1.0 + std::fmax(std::fmax(std::fabs((double)c.ax), std::fabs((double)c.ay)), std::fabs((double)c.az)) +
                        std::fmax(std::fmax(std::fabs((double)c.bx), std::fabs((double)c.by)), std::fabs((double)c.bz));
     const double Rt = std::fabs((double)c.r) * (1.0 + 1e-3) + 1e-5 * mag;
     b.capt[k][0] = abx; b.capt[k][1] = aby; b.capt[k][2] = abz;
+    b.capx[k][0] = abx; b.capx[k][1] = aby; b.capx[k][2] = abz; b.capx[k][3] = l2; b.capx[k][4] = c.r * c.r;
+    b.capx[k][5] = b.capx[k][6] = b.capx[k][7] = 0.0f;
     b.capt[k][3] = l2 > 0.0f ? 1.0f / l2 : 0.0f;
     b.capt[k][4] = std::nextafter((float)(Rt * Rt), INFINITY);
     b.capt[k][5] = std::nextafter(std::sqrt(b.capt[k][4]), INFINITY);         // >= sqrt(r2_tight): the surface the temporal bound measures from

@@ -596,6 +596,46 @@ def test_stream_kernel_capsules_bit_exact(caps, S, N, sphere):
         assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
 
 
+@pytest.mark.parametrize("S,N", [(2100, 32), (1300, 24), (3000, 4), (999, 13)])
+def test_stream_kernel_capsules_temporal_bound_bit_exact(S, N):
+    """The temporal bound in front of the capsule tests (a lane re-tests only when its last measured distance has been used
+    up by the rest lengths stepped since): strands blown by wind into capsules that only their outer vertices reach, with
+    rest lengths that vary wildly along a strand and from strand to strand (a few segments ten times the others, some
+    almost zero), over enough steps for whole strands to arrive from far away. Any skipped test that mattered shows as a
+    vertex left inside a capsule, i.e. as a mismatch."""
+    pos, vel = ragged_state(S, N, seed=7)
+    rng = np.random.default_rng(11)
+    f = rng.choice(np.array([0.02, 0.5, 1.0, 1.0, 1.0, 2.0, 10.0], np.float32), size=S * N)
+    pos[:, 3] = (pos[:, 3] * f).astype(np.float32)
+    caps = [((-0.4, -1.9, 0.3), (0.9, -2.3, -0.2), 0.35), ((1.4, -1.0, 0.2), (1.6, -0.1, 0.5), 0.3), ((1.6, -1.9, 0.9), (1.6, -1.9, 0.9), 0.45)]
+    wind = (2.5, -1.0, 0.7)
+    par, gcfg = _capsule_params(caps, dt=float(DT), scale=1.45, sphere=SPHERE)
+    for i, x in enumerate(wind):
+        par.wind[i] = x
+        gcfg.wind[i] = x
+    rp, rv = pos.copy(), vel.copy()
+    nsteps = 60
+    for _ in range(nsteps):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        assert sim.kernel_kind == 0
+        sim.upload(pos, vel)
+        for _ in range(nsteps):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    assert_bit_equal(gp, rp, "positions")
+    assert_bit_equal(gv, rv, "velocities")
+    x = rp[:, :3].astype(np.float64).reshape(S, N, 3)[:, 1:].reshape(-1, 3)
+    on = np.zeros(len(x), bool)
+    for a, b, r in caps:
+        a, b = np.array(a), np.array(b)
+        ab = b - a
+        t = np.clip((x - a) @ ab / max(ab @ ab, 1e-30), 0, 1) if ab @ ab > 0 else np.zeros(len(x))
+        on |= np.abs(np.linalg.norm(x - (a + t[:, None] * ab), axis=1) - r) < 1e-5
+    assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
+
+
 @pytest.mark.parametrize("sphere", [(0.0, 0.0, 0.0, 5.0), (0.0, 0.0, 0.0, 0.0), (0.3, 2.0, 0.1, 1.2), (0.0, 0.0, 0.0, 1.0e-3), (1.0e3, 0.0, 0.0, 1.0)])
 @pytest.mark.parametrize("caps", ["arms", "shell", "overlap"])
 def test_stream_kernel_capsules_any_sphere_bit_exact(caps, sphere):

@@ -10,6 +10,6 @@ cp barbu_b200/lib/libbarbu_hair_stats.so barbu_b200/lib/libbarbu_hair.so
 for m in exact fast; do echo "stats arms $m"; timeout 300 python tests/reports/config3.py --caps arms --frames 1 --settle 30 --math $m --check 0 --log2s 20 2>&1 | grep BH_STATS | tail -1; done
 cp /tmp/prod.so barbu_b200/lib/libbarbu_hair.so
 for m in exact fast; do run none $m prod; run far $m prod; CHECK=2048 run arms $m prod; done
-for v in "$@"; do cp barbu_b200/lib/libbarbu_hair_$v.so barbu_b200/lib/libbarbu_hair.so; for m in exact fast; do run arms $m $v; done; done
+for v in "$@"; do cp barbu_b200/lib/libbarbu_hair_$v.so barbu_b200/lib/libbarbu_hair.so; for m in exact fast; do run far $m $v; run arms $m $v; done; done
 cp /tmp/prod.so barbu_b200/lib/libbarbu_hair.so
 } | tee gpurun_out/capexp.txt
