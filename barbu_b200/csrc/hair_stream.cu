@@ -55,7 +55,10 @@ typedef unsigned long long u64;
 #define BH_DRAG 1
 #endif
 #ifndef BH_CAPS_ONE_BODY
-#define BH_CAPS_ONE_BODY 1
+#define BH_CAPS_ONE_BODY 0
+#endif
+#ifndef BH_CAPS_SINGLE
+#define BH_CAPS_SINGLE 2
 #endif
 #ifndef BH_CAPS_PAIRS
 #define BH_CAPS_PAIRS 1
@@ -224,6 +227,10 @@ __device__ __forceinline__ V3 root_transform(V3 p) {
            M::add(M::add(zx, M::mul(1.0f, p.y)), M::add(zz, z1)),
            M::add(M::add(zx, zy), M::add(M::mul(1.0f, p.z), z1)) };
 }
+
+// Capsule variant: ONE step variant (every step hands its positions on through P, as a step after a push-out does) instead of
+// a free and a contact variant. 1: exact profile only, 2: both profiles. See stream_chunk.
+template <class PM> __device__ __forceinline__ constexpr bool caps_single() { return BH_CAPS_SINGLE == 2 || (BH_CAPS_SINGLE == 1 && PM::kRangeChecked); }
 
 // Pipeline registers. Pair a holds stages a (lo) and a + 4 (hi).
 //
@@ -528,7 +535,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
   };
   bool maybe_hit = true;                                                      // warp-uniform
   float mnc = 0.f, mxc = 0.f;                                                 // smallest / (capsule variant) largest |p - c|^2 of this lane
-  if (PM::kTwoStageTest && !SEP) {
+  if (PM::kTwoStageTest && (!SEP || (CAPS && caps_single<PM>()))) {
     // The exact squared distance (five packed operations per pair, the reference's rounding sequence) is only NEEDED by a
     // vertex that is pushed out; whether any vertex is, a contracted sum of squares (three operations) decides for all
     // but the warps within 2^-20 relative of the surface: both sums carry at most three roundings of at most the true value,
@@ -632,7 +639,16 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
 #ifdef BH_STATS   // a skipped test that would have let a lane through (must stay zero)
     if (!any_cap) { float d_; if (caps_tight_touch(a, D, d_) && (threadIdx.x & 31) == 0) BH_STAT(14, 1); }
 #endif
-    if (!any_cap) { s.heldCap = false; return false; }
+    if (!any_cap) {
+      s.heldCap = false;
+      if (caps_single<PM>()) {                              // one step variant: every step hands its positions on through P
+#pragma unroll
+        for (int q = 0; q < 4; ++q) C[q] = D[q];
+        enter_through_P();
+        return true;
+      }
+      return false;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) C[q] = D[q];
   } else {
@@ -672,7 +688,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     BH_T1(11, t3);
   }
   s.heldCap = any_cap && !root_in_stage<RS>(j, 7);                          // conservative: recomputing without a hit is a no-op
-  if (any_hit || any_cap) enter_through_P();
+  if (any_hit || any_cap || caps_single<PM>()) enter_through_P();
   return any_hit || any_cap;
 }
 
@@ -687,6 +703,12 @@ __device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pi
   // allocates and lays out better than one loop that picks its body every step — free step 228 -> 221 instructions, contact
   // step 362 -> 359, configs[1] exact 0.4977 -> 0.4913 ms per launch (A/B on one box).
   int j = 0;
+  if (CAPS && caps_single<PM>()) {
+#pragma unroll 1
+    for (; j < kK; ++j) stream_step<PM, ORIGIN, RS, true, CAPS>(a, nz, s, j + joff, (fin_mask >> j) & 1u, bP + (j ^ sw), bV + (j ^ sw), myR + j * 32);
+    sep = true;
+    return;
+  }
 #pragma unroll 1
   for (;;) {
     if (!sep) {
