@@ -804,8 +804,8 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) {
         tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence();
 #ifdef BH_STATS
-        printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: tested %llu (unused %llu) touched %llu | cycles: (unused %llu) test %llu slow %llu recompute %llu warp-total %llu | skipped tests that would have passed %llu\n", g_stats[0], g_stats[1], g_stats[2],
-               g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[7], g_stats[8], g_stats[9], g_stats[10], g_stats[11], g_stats[12], g_stats[13], g_stats[14]);
+        printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: tested %llu touched %llu | cycles: test %llu chain %llu recompute %llu warp-total %llu | skipped tests that would have passed %llu\n",
+               g_stats[0], g_stats[1], g_stats[2], g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[8], g_stats[10], g_stats[11], g_stats[12], g_stats[13], g_stats[14]);
         for (int i = 0; i < 16; ++i) g_stats[i] = 0;
 #endif
       }
