@@ -746,6 +746,10 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   // (-0.0f, -0.0f), read from device memory: a value ptxas can neither fold into the packed products (it would then
   // contract them with the following add) nor re-load from the constant bank in the middle of the step
   const u64 nz = *reinterpret_cast<const u64*>(tile_counter + 2);
+  // Programmatic dependent launch: the next launch of the stream may move onto an SM as soon as this launch's blocks leave it
+  // and run its prologue (shared-memory carve-up, barrier init) there; it waits below, before its first tile, for this grid to
+  // have completed and flushed. Hides the launch gap behind the tail of the previous launch; changes nothing else.
+  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -815,6 +819,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
       }
     }
   };
+  asm volatile("griddepcontrol.wait;" ::: "memory");                        // the state (and the scheduler words) as the previous launch left them
   int tC = grab(), cC = 0;
   if (tC < 0) { leave(); return; }
   if (FUSED) tC *= gtiles;
@@ -1074,8 +1079,15 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   if (occ_cap > 0 && occ_cap < per_sm) per_sm = occ_cap;
   const long long resident = (long long)sms * per_sm;
   if (blocks > resident) blocks = resident;
-  kernel<<<(unsigned)blocks, kThreads, kSmemBytes, stream>>>(a, mapP, mapV, tile_counter);
-  return cudaGetLastError();
+  static const bool pdl = [] { const char* e = getenv("BH_STREAM_PDL"); return !e || atoi(e) != 0; }();   // tuning knob: 0 = plain stream order
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kernel, a, mapP, mapV, tile_counter);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // Exhaustive check of the branch-free inverse square roots against the IEEE builtins: every finite binary32
