@@ -48,12 +48,6 @@ namespace {
 
 typedef unsigned long long u64;
 
-#ifndef BH_FINROOT_STORE
-#define BH_FINROOT_STORE 0
-#endif
-#ifndef BH_DRAG
-#define BH_DRAG 1
-#endif
 #ifndef BH_CAPS_ONE_BODY
 #define BH_CAPS_ONE_BODY 0
 #endif
@@ -425,7 +419,7 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
       if (set1) s.rootV[1] = rv; else s.rootV[0] = rv;
     } else {
       float4 V = Vin;
-      if (BH_DRAG && a.use_drag) { V.x = M::mul(V.x, a.keep); V.y = M::mul(V.y, a.keep); V.z = M::mul(V.z, a.keep); }
+      if (a.use_drag) { V.x = M::mul(V.x, a.keep); V.y = M::mul(V.y, a.keep); V.z = M::mul(V.z, a.keep); }
       x = { __fmaf_rn(a.dt2, a.fx, __fmaf_rn(a.dt, V.x, Pin.x)), __fmaf_rn(a.dt2, a.fy, __fmaf_rn(a.dt, V.y, Pin.y)),
             __fmaf_rn(a.dt2, a.fz, __fmaf_rn(a.dt, V.z, Pin.z)) };         // cs:181-182
     }
@@ -496,17 +490,9 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
       }
       const float4 oP = make_float4(fp.x, fp.y, fp.z, rest_out);
       float4 oV = make_float4(fw.x, fw.y, fw.z, 0.f);
-#if BH_FINROOT_STORE
-      *slotP = oP;
-      *slotV = oV;
-      // a root is neither moved nor reflected: its velocity overwrites the slot (warp-uniform, one step per strand; opaque so
-      // that the compiler does not turn it back into three selects in every step)
-      if (fin_root) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(smem_u32(slotV)), "f"(rootV_out.x), "f"(rootV_out.y), "f"(rootV_out.z), "f"(0.f) : "memory");
-#else
       if (fin_root) oV = make_float4(rootV_out.x, rootV_out.y, rootV_out.z, 0.f);   // a root is neither moved nor reflected
       *slotP = oP;
       *slotV = oV;
-#endif
     }
     s.X[q] = D[q];
   }
@@ -626,9 +612,6 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     s.slack -= __fmaf_rn(s.lmax, 1.0009765625f, eb);
     any_cap = __any_sync(0xffffffffu, in_shell && !(s.slack > 0.f));
   }
-#if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 1   // timing experiments only (results are wrong): drop everything behind level 0 / 1 / 2
-  any_cap = false;
-#endif
 #ifdef BH_STATS
   if ((threadIdx.x & 31) == 0) BH_STAT(6, any_cap);
 #endif
@@ -666,9 +649,6 @@ __device__ __forceinline__ bool stream_step(const StepArgs& a, const u64 nz, Pip
     any_cap = cmask != 0u;
     BH_T1(10, t2);
   }
-#if defined(BH_EXP_CAPS) && BH_EXP_CAPS == 3
-  any_cap = false;
-#endif
 #ifdef BH_STATS
   if ((threadIdx.x & 31) == 0) BH_STAT(8, any_cap);
 #endif
