@@ -636,6 +636,62 @@ def test_stream_kernel_capsules_temporal_bound_bit_exact(S, N):
     assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
 
 
+def _random_capsule_scene(seed):
+    """A random scene for the capsule variant: 1-8 capsules of random size scattered through the volume the hair sweeps (some
+    degenerate, some huge, some tiny), random wind and drag, random sphere, rest lengths scaled per vertex, random shape."""
+    rng = np.random.default_rng(seed)
+    S = int(rng.integers(200, 1500)); N = int(rng.choice([4, 5, 8, 13, 16, 24, 32, 40]))
+    pos, vel = ragged_state(S, N, seed=seed)
+    f = rng.choice(np.array([0.05, 0.5, 1.0, 1.0, 1.0, 1.5, 4.0], np.float32), size=S * N)
+    pos[:, 3] = (pos[:, 3] * f).astype(np.float32)
+    ncaps = int(rng.integers(1, 9))
+    caps = []
+    for _ in range(ncaps):
+        a = rng.uniform(-2.2, 2.2, 3)
+        kind = rng.integers(0, 5)
+        b = a if kind == 0 else a + rng.uniform(-1.0, 1.0, 3) * (3.0 if kind == 1 else 0.8)
+        r = float(rng.choice([0.02, 0.1, 0.25, 0.4, 0.9]))
+        caps.append((tuple(float(x) for x in a), tuple(float(x) for x in b), r))
+    sphere = (float(rng.uniform(-0.1, 0.1)), float(rng.uniform(-0.1, 0.1)), float(rng.uniform(-0.1, 0.1)), float(rng.choice([0.0, 0.9, 0.98, 1.05])))
+    if rng.integers(0, 3) == 0:
+        sphere = (0.0, 0.0, 0.0, sphere[3])                                   # the origin-centred variant of the kernel
+    wind = tuple(float(x) for x in rng.uniform(-3.0, 3.0, 3))
+    drag = float(rng.choice([0.0, 0.0, 0.03]))
+    scale = float(rng.choice([1.0, 1.45, 2.0]))
+    return S, N, pos, vel, caps, sphere, wind, drag, scale
+
+
+def run_capsule_scene(seed, nsteps=40):
+    """Steps a random capsule scene on the device and on the oracle; returns the number of differing words (0 = bit-equal)."""
+    S, N, pos, vel, caps, sphere, wind, drag, scale = _random_capsule_scene(seed)
+    par, gcfg = _capsule_params(caps, dt=float(DT), scale=scale, sphere=sphere)
+    par.drag = gcfg.drag = drag
+    for i, x in enumerate(wind):
+        par.wind[i] = x
+        gcfg.wind[i] = x
+    rp, rv = pos.copy(), vel.copy()
+    for _ in range(nsteps):
+        po.step(rp, rv, S, N, par, nthreads=16)
+    with bb.HairSim(S, N) as sim:
+        sim.set_params(gcfg)
+        sim.upload(pos, vel)
+        kind = sim.kernel_kind
+        for _ in range(nsteps):
+            sim.step(float(DT), 1)
+        gp, gv, _ = sim.download()
+    diff = int((gp.view(np.uint32) != rp.view(np.uint32)).sum() + (gv.view(np.uint32) != rv.view(np.uint32)).sum())
+    return diff, kind, (S, N, len(caps))
+
+
+@pytest.mark.parametrize("seed", range(1000, 1024))
+def test_stream_kernel_capsules_random_scenes_bit_exact(seed):
+    """Fuzz of the capsule variant's conservative machinery (shell, temporal bound, capsule-shaped bound, packed chain): random
+    scenes, 40 steps each, bit-equal to the oracle. tests/reports/capsule_fuzz.py runs the same generator over more seeds."""
+    diff, kind, shape = run_capsule_scene(seed)
+    assert kind == 0, "capsules must not leave the streaming kernel"
+    assert diff == 0, f"seed {seed} {shape}: {diff} words differ"
+
+
 @pytest.mark.parametrize("sphere", [(0.0, 0.0, 0.0, 5.0), (0.0, 0.0, 0.0, 0.0), (0.3, 2.0, 0.1, 1.2), (0.0, 0.0, 0.0, 1.0e-3), (1.0e3, 0.0, 0.0, 1.0)])
 @pytest.mark.parametrize("caps", ["arms", "shell", "overlap"])
 def test_stream_kernel_capsules_any_sphere_bit_exact(caps, sphere):
