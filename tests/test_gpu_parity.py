@@ -732,6 +732,8 @@ def test_stream_kernel_capsules_fast_profile_close_to_exact():
             out[math], _, _ = sim.download()
     err = rel_err(out[bb.BH_MATH_FAST], out[bb.BH_MATH_EXACT])
     assert np.percentile(err, 99.9) <= 1e-5, f"p99.9 {np.percentile(err, 99.9):.3e}"
+    # ... and the MAXIMUM over all vertices, no vertex set aside (measured: 1.1e-6)
+    assert err.max() <= 1e-5, f"max {err.max():.3e}"
 
 
 # ---- BASELINE.json sizes: size-independent properties + sampled strands against the oracle -------------
