@@ -121,6 +121,7 @@ constexpr u64 kHalf2 = 0x3f0000003f000000ull;
 
 #ifdef BH_STATS   // debug build only (tools/stats_build.sh): contact statistics of the step loop, printed by the last warp of a launch
 __device__ unsigned long long g_stats[16];
+__device__ unsigned long long g_span[4];       // first start / last end of a warp (globaltimer ns), sum of the warps' busy ns, warps
 __device__ __forceinline__ unsigned long long* bh_warp_stats() {           // per-warp counters in shared memory, flushed once per launch
   __shared__ unsigned long long w[8][16];
   return w[threadIdx.x >> 5];
@@ -794,7 +795,10 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
 #ifdef BH_STATS
         printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: tested %llu touched %llu | cycles: test %llu chain %llu recompute %llu warp-total %llu | skipped tests that would have passed %llu\n",
                g_stats[0], g_stats[1], g_stats[2], g_stats[3], g_stats[4], g_stats[5], g_stats[6], g_stats[8], g_stats[10], g_stats[11], g_stats[12], g_stats[13], g_stats[14]);
+        printf("BH_SPAN launch %llu ns, warps %llu, mean busy %llu ns (%.2f %% of the span idle)\n", g_span[1] - g_span[0], g_span[3], g_span[2] / g_span[3],
+               100.0 - 100.0 * (double)g_span[2] / ((double)(g_span[1] - g_span[0]) * (double)g_span[3]));
         for (int i = 0; i < 16; ++i) g_stats[i] = 0;
+        for (int i = 0; i < 4; ++i) g_span[i] = 0;
 #endif
       }
     }
@@ -846,6 +850,9 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   if (lane == 0) for (int i = 0; i < 16; ++i) bh_warp_stats()[i] = 0;
 #endif
   BH_T0(t_warp);
+#ifdef BH_STATS
+  unsigned long long ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+#endif
   for (;; ++q) {
     const int b = q & 1;
     const bool live = tC >= 0;                                              // false: the drain chunk after the last tile
@@ -879,6 +886,11 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   BH_T1(13, t_warp);
 #ifdef BH_STATS
   if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_stats[i], bh_warp_stats()[i]);
+  if (lane == 0) {                                                          // how much of the launch the warps spend without a tile (tail)
+    unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    if (g_span[0] == 0ull) atomicCAS(&g_span[0], 0ull, ns0);
+    atomicMin(&g_span[0], ns0); atomicMax(&g_span[1], ns1); atomicAdd(&g_span[2], ns1 - ns0); atomicAdd(&g_span[3], 1ull);
+  }
 #endif
   leave();
 }
