@@ -636,15 +636,15 @@ def test_stream_kernel_capsules_temporal_bound_bit_exact(S, N):
     assert on.any(), "no vertex rests on a capsule: the test does not cover the push-out"
 
 
-def _random_capsule_scene(seed):
+def _random_capsule_scene(seed, capsules=True):
     """A random scene for the capsule variant: 1-8 capsules of random size scattered through the volume the hair sweeps (some
     degenerate, some huge, some tiny), random wind and drag, random sphere, rest lengths scaled per vertex, random shape."""
     rng = np.random.default_rng(seed)
-    S = int(rng.integers(200, 1500)); N = int(rng.choice([4, 5, 8, 13, 16, 24, 32, 40]))
+    S = int(rng.integers(200, 1500)); N = int(rng.choice([4, 5, 8, 13, 16, 24, 32, 40]) if capsules else rng.integers(1, 71))
     pos, vel = ragged_state(S, N, seed=seed)
     f = rng.choice(np.array([0.05, 0.5, 1.0, 1.0, 1.0, 1.5, 4.0], np.float32), size=S * N)
     pos[:, 3] = (pos[:, 3] * f).astype(np.float32)
-    ncaps = int(rng.integers(1, 9))
+    ncaps = int(rng.integers(1, 9)) if capsules else 0
     caps = []
     for _ in range(ncaps):
         a = rng.uniform(-2.2, 2.2, 3)
@@ -661,10 +661,10 @@ def _random_capsule_scene(seed):
     return S, N, pos, vel, caps, sphere, wind, drag, scale
 
 
-def run_capsule_scene(seed, nsteps=40, fused_substeps=0):
+def run_capsule_scene(seed, nsteps=40, fused_substeps=0, capsules=True):
     """Steps a random capsule scene on the device and on the oracle; returns the number of differing words (0 = bit-equal).
     fused_substeps = k > 0: the device runs frames of k substeps as ONE launch each (fusion forced), nsteps // k frames."""
-    S, N, pos, vel, caps, sphere, wind, drag, scale = _random_capsule_scene(seed)
+    S, N, pos, vel, caps, sphere, wind, drag, scale = _random_capsule_scene(seed, capsules)
     k = max(fused_substeps, 1)
     h = float(np.float32(DT) / np.float32(k)) if k > 1 else float(DT)
     par, gcfg = _capsule_params(caps, dt=h, scale=scale, sphere=sphere)
@@ -689,6 +689,14 @@ def run_capsule_scene(seed, nsteps=40, fused_substeps=0):
     diff = int(((gp.view(np.uint32) != rp.view(np.uint32)) & ~(np.isnan(gp) & np.isnan(rp))).sum()
                + ((gv.view(np.uint32) != rv.view(np.uint32)) & ~(np.isnan(gv) & np.isnan(rv))).sum())
     return diff, kind, (S, N, len(caps))
+
+
+@pytest.mark.parametrize("seed", range(3000, 3016))
+def test_random_scenes_without_capsules_bit_exact(seed):
+    """The same fuzz without capsules (the reference's own collider set: one sphere), 1-70 vertices per strand, whatever
+    kernel the shape selects; odd seeds run frames of 3 substeps (fused where the shape allows it)."""
+    diff, kind, shape = run_capsule_scene(seed, nsteps=39, fused_substeps=3 if seed % 2 else 0, capsules=False)
+    assert diff == 0, f"seed {seed} {shape}: kernel kind {kind}, {diff} words differ"
 
 
 @pytest.mark.parametrize("seed", range(2000, 2008))
