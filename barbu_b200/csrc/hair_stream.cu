@@ -58,16 +58,24 @@ typedef unsigned long long u64;
 #define BH_CAPS_PAIRS 1
 #endif
 constexpr int kK = 8;                            // constraint iterations == pipeline depth == vertices per chunk
+// Warps per block is a LAUNCH parameter (the kernel reads blockDim): small shards get blocks of kWarps warps, three to an SM, so
+// that their tiles spread over the SMs; a shard that fills the GPU anyway gets ONE block of kWarpsBig warps per SM — the same
+// twelve resident warps, 1 % faster in the exact profile (0.4903 -> 0.4860 ms per launch at configs[1], fused frame 1.922 ->
+// 1.900 ms; A/B on one box). The HBM-bound fast launch keeps the small blocks (0.3398 vs 0.3409 ms).
 #ifndef BH_STREAM_WARPS
 #define BH_STREAM_WARPS 4
 #endif
+#ifndef BH_STREAM_WARPS_BIG
+#define BH_STREAM_WARPS_BIG 12
+#endif
 constexpr int kWarps = BH_STREAM_WARPS;
-constexpr int kThreads = kWarps * 32;
+constexpr int kWarpsBig = BH_STREAM_WARPS_BIG;
+constexpr int kMaxThreads = (kWarpsBig > kWarps ? kWarpsBig : kWarps) * 32;
 constexpr int kPlaneTile = 32 * 128;             // bytes of one plane of one chunk: 32 strands x 8 vertices x 16 B
 constexpr int kStageBytes = 2 * kPlaneTile;      // position + velocity
 constexpr int kWarpTileBytes = 2 * kStageBytes;  // two stages
 constexpr int kRingBytes = kK * 32 * 4;          // rest lengths of the 8 vertices in flight, [slot][lane]
-constexpr int kSmemBytes = 1024 /* alignment slack */ + kWarps * (kWarpTileBytes + kRingBytes) + kWarps * 2 * 8;
+constexpr int smem_bytes(int warps) { return 1024 /* alignment slack */ + warps * (kWarpTileBytes + kRingBytes) + warps * 2 * 8; }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -123,7 +131,7 @@ constexpr u64 kHalf2 = 0x3f0000003f000000ull;
 __device__ unsigned long long g_stats[16];
 __device__ unsigned long long g_span[4];       // first start / last end of a warp (globaltimer ns), sum of the warps' busy ns, warps
 __device__ __forceinline__ unsigned long long* bh_warp_stats() {           // per-warp counters in shared memory, flushed once per launch
-  __shared__ unsigned long long w[8][16];
+  __shared__ unsigned long long w[16][16];
   return w[threadIdx.x >> 5];
 }
 #define BH_STAT(i, v) (bh_warp_stats()[i] += (unsigned long long)(v))
@@ -718,10 +726,7 @@ __device__ __forceinline__ void stream_chunk(const StepArgs& a, const u64 nz, Pi
 // FUSED: the launch runs StepArgs::passes steps over groups of tiles (frame-level substep fusion); its own instantiation, so
 // that the plain one-step launch keeps its code (and registers) exactly.
 template <class PM, bool ORIGIN, int NS, bool CAPS, bool FUSED>
-#ifndef BH_STREAM_MINB
-#define BH_STREAM_MINB 3
-#endif
-__global__ void __launch_bounds__(kThreads, BH_STREAM_MINB)
+__global__ void __launch_bounds__(kMaxThreads, 1)                           // 384 threads: 168 registers, as with three blocks of 128
 hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap mapP,
                         const __grid_constant__ CUtensorMap mapV, unsigned int* tile_counter) {
   // (-0.0f, -0.0f), read from device memory: a value ptxas can neither fold into the packed products (it would then
@@ -734,12 +739,13 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // 128B-swizzled tiles repeat every 1024 B
   unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
   unsigned char* tiles = gen + warp * kWarpTileBytes;                       // [stage][plane][32 x 128 B]
-  float* ring = reinterpret_cast<float*>(gen + kWarps * kWarpTileBytes + warp * kRingBytes);
+  float* ring = reinterpret_cast<float*>(gen + nwarps * kWarpTileBytes + warp * kRingBytes);
   const uint32_t tiles_s = base + warp * kWarpTileBytes;
-  const uint32_t bar_s = base + kWarps * (kWarpTileBytes + kRingBytes) + warp * 16;
+  const uint32_t bar_s = base + nwarps * (kWarpTileBytes + kRingBytes) + warp * 16;
 
   const int chunks = NS == 8 ? (a.nverts + kK - 1) / kK : 1;                // per row; the last one may be ragged (see tip_step)
   const long long nrows = NS == 8 ? a.nstrands : a.nstrands / 2;
@@ -790,7 +796,7 @@ hair_step_stream_kernel(const __grid_constant__ StepArgs a, const __grid_constan
   auto leave = [&]() {
     if (lane == 0) {
       __threadfence();
-      if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * kWarps - 1) {
+      if (atomicAdd(tile_counter + 1, 1u) == gridDim.x * (unsigned)nwarps - 1u) {
         tile_counter[0] = 0u; tile_counter[1] = 0u; __threadfence();
 #ifdef BH_STATS
         printf("BH_STATS steps %llu hit %llu pairs %llu stages %llu lanes %llu sep %llu | caps: tested %llu touched %llu | cycles: test %llu chain %llu recompute %llu warp-total %llu | skipped tests that would have passed %llu\n",
@@ -934,7 +940,7 @@ bool make_plane_map(CUtensorMap* map, float4* plane, long long nstrands, int nve
             CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
 }
 
-struct DeviceInfo { int sms = 0; bool ready[24] = {}; int blocks_per_sm[24] = {}; };
+struct DeviceInfo { int sms = 0; bool ready[24] = {}; int blocks_per_sm[24] = {}; int big_blocks_per_sm[24] = {}; };
 
 // Bounds in front of the exact capsule arithmetic. Each is widened by 1e-3 relative plus an absolute term — orders of
 // magnitude above the fp32 rounding of either the bound or the exact test it guards, so "outside the bound" implies "the
@@ -1023,18 +1029,19 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   auto kernel = hair_step_stream_kernel<PM, ORIGIN, NS, CAPS, FUSED>;
-  int sms = 0, blocks_per_sm = 0;                                           // copies taken under the lock
+  int sms = 0, blocks_per_sm = 0, big_blocks_per_sm = 0;                    // copies taken under the lock
   {
     std::lock_guard<std::mutex> g(mu);
     DeviceInfo& di = info[dev];
     if (!di.ready[variant]) {
       if ((e = cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess) return e;
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.blocks_per_sm[variant], kernel, kThreads, kSmemBytes)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kWarpsBig > kWarps ? kWarpsBig : kWarps))) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.blocks_per_sm[variant], kernel, kWarps * 32, smem_bytes(kWarps))) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.big_blocks_per_sm[variant], kernel, kWarpsBig * 32, smem_bytes(kWarpsBig))) != cudaSuccess) return e;
       if (di.blocks_per_sm[variant] < 1) return cudaErrorLaunchOutOfResources;
       di.ready[variant] = true;
     }
-    sms = di.sms; blocks_per_sm = di.blocks_per_sm[variant];
+    sms = di.sms; blocks_per_sm = di.blocks_per_sm[variant]; big_blocks_per_sm = di.big_blocks_per_sm[variant];
   }
   // Tensor maps are pure functions of (plane address, shape): keep the last few so a frame of substeps on the same
   // shard (or the slices of bh_step_host) does not re-encode them at every launch. Process-wide and never invalidated on
@@ -1065,15 +1072,22 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   a.group_tiles = a.passes > 1 ? fusion_group_tiles(a.nverts) : 1;
   if (a.passes > 1 && ntiles < a.group_tiles) return cudaErrorInvalidValue;   // callers ask stream_fusion_eligible() first
   const long long ngroups = ntiles / a.group_tiles;
-  long long blocks = (ngroups + kWarps - 1) / kWarps;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
-  int per_sm = blocks_per_sm;
+  static const bool big_ok = [] { const char* e = getenv("BH_STREAM_BIG_BLOCKS"); return !e || atoi(e) != 0; }();    // tuning knob: 0 = small blocks always
+  // one big block per SM when the shard gives every warp of every SM at least two groups and the big block holds no fewer
+  // warps than the small ones together; otherwise small blocks, which spread a small shard over the SMs
+  // (exact profile and fused frames: the HBM-bound fast launch measures 0.3 % slower with it)
+  const bool big = big_ok && (PM::kRangeChecked || FUSED) && occ_cap == 0 && big_blocks_per_sm >= 1 && big_blocks_per_sm * kWarpsBig >= blocks_per_sm * kWarps &&
+                   ngroups >= 2ll * sms * big_blocks_per_sm * kWarpsBig;
+  const int warps = big ? kWarpsBig : kWarps;
+  long long blocks = (ngroups + warps - 1) / warps;
+  int per_sm = big ? big_blocks_per_sm : blocks_per_sm;
   if (occ_cap > 0 && occ_cap < per_sm) per_sm = occ_cap;
   const long long resident = (long long)sms * per_sm;
   if (blocks > resident) blocks = resident;
   static const bool pdl = [] { const char* e = getenv("BH_STREAM_PDL"); return !e || atoi(e) != 0; }();   // tuning knob: 0 = plain stream order
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(warps * 32); cfg.dynamicSmemBytes = smem_bytes(warps); cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
