@@ -1073,12 +1073,12 @@ cudaError_t launch_stream_tf(const StepArgs& a_in, cudaStream_t stream, unsigned
   if (a.passes > 1 && ntiles < a.group_tiles) return cudaErrorInvalidValue;   // callers ask stream_fusion_eligible() first
   const long long ngroups = ntiles / a.group_tiles;
   static const int occ_cap = [] { const char* e = getenv("BH_STREAM_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();   // tuning knob
-  static const bool big_ok = [] { const char* e = getenv("BH_STREAM_BIG_BLOCKS"); return !e || atoi(e) != 0; }();    // tuning knob: 0 = small blocks always
+  static const int big_ok = [] { const char* e = getenv("BH_STREAM_BIG_BLOCKS"); return e ? atoi(e) : 1; }();        // tuning knob: 0 = small blocks always, 2 = big blocks for every shape and profile (tests)
   // one big block per SM when the shard gives every warp of every SM at least two groups and the big block holds no fewer
   // warps than the small ones together; otherwise small blocks, which spread a small shard over the SMs
   // (exact profile and fused frames: the HBM-bound fast launch measures 0.3 % slower with it)
-  const bool big = big_ok && (PM::kRangeChecked || FUSED) && occ_cap == 0 && big_blocks_per_sm >= 1 && big_blocks_per_sm * kWarpsBig >= blocks_per_sm * kWarps &&
-                   ngroups >= 2ll * sms * big_blocks_per_sm * kWarpsBig;
+  const bool big = big_ok && occ_cap == 0 && big_blocks_per_sm >= 1 && big_blocks_per_sm * kWarpsBig >= blocks_per_sm * kWarps &&
+                   (big_ok == 2 || ((PM::kRangeChecked || FUSED) && ngroups >= 2ll * sms * big_blocks_per_sm * kWarpsBig));
   const int warps = big ? kWarpsBig : kWarps;
   long long blocks = (ngroups + warps - 1) / warps;
   int per_sm = big ? big_blocks_per_sm : blocks_per_sm;

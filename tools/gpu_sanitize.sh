@@ -6,4 +6,8 @@ for tool in memcheck racecheck initcheck synccheck; do
   echo "== $tool" >> $OUT
   timeout 900 compute-sanitizer --tool $tool python tests/reports/sanitizer_case.py 2>&1 | grep -v "^=========$" | grep "^ok\|^tess\|ERROR SUMMARY\|RACECHECK SUMMARY\|Error\|error\|hazard\|Traceback\|assert" | head -60 >> $OUT
 done
+echo "== memcheck + racecheck with BH_STREAM_BIG_BLOCKS=2 (one block of 12 warps per SM forced for every launch)" >> $OUT
+for tool in memcheck racecheck; do
+  BH_STREAM_BIG_BLOCKS=2 timeout 900 compute-sanitizer --tool $tool python tests/reports/sanitizer_case.py 2>&1 | grep -v "^=========$" | grep "ERROR SUMMARY\|RACECHECK SUMMARY\|Error\|error\|hazard\|Traceback\|assert" | head -20 >> $OUT
+done
 cat $OUT
